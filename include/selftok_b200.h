@@ -1,0 +1,166 @@
+/*
+ * selftok_b200.h — C ABI of the B200-native SelftokTokenizer encode / decode hot path.
+ *
+ * The reference (selftok-team/SelftokTokenizer) is pure Python; the boundary it exposes for this path is the
+ * class API of mimogpt/infer/SelftokPipeline.py (SelftokPipeline.encoding :210-225, .decoding :227-294,
+ * .decoding_with_renderer :296-322) and it has no FFI of its own.  This header is what a maintainer binds
+ * (ctypes) to replace the torch modules behind those three methods:
+ *
+ *   reference call site (file:line)                                     replaced by
+ *   ------------------------------------------------------------------  ---------------------------------------
+ *   SelftokPipeline.__init__  ImageTokenizer(**cfg.tokenizer.params)     selftok_create
+ *       mimogpt/infer/SelftokPipeline.py:168
+ *   self.model.load_state_dict(state_dict, strict=False)   :190-195      selftok_load_tensor (one call per key)
+ *   RectifiedFlow(50, ...).make_schedule / DiTi_cont      :201-204       selftok_set_schedule + selftok_finalize
+ *       sd3/rectified_flow.py:66-80, diti_utils.py:84-110
+ *   self.model.encoder(x_0, d=None)                        :220-221      selftok_encode
+ *       models_ours.py:204-251 (16 x DualBlock modules.py:310-327, VectorQuantize vector_quantize_pytorch.py:811-876)
+ *   CosineSimCodebook.forward eval (einsum+argmax+gather)                selftok_vq_argmax
+ *       vector_quantize_pytorch.py:525-563,580
+ *   quantizer.get_output_from_indices + final_layer_norm3  :236-240      selftok_lookup
+ *   flow.p_sample_loop(self.model.model, ...)              :277-282      selftok_decode
+ *       sd3/rectified_flow.py:165-309 driving MMDiT.forward sd3/mmdit.py:992-1101
+ *   self.model.model(y=None, encoder_hidden_states=outs_q) :310          selftok_render
+ *       MMDiT_Renderer.forward sd3/mmdit.py:1511-1620
+ *
+ * Conventions: every function returns 0 on success and a negative selftok_status otherwise (never throws,
+ * never aborts); selftok_last_error() returns a thread-local description of the last failure.  Pointers named
+ * *_dev are CUDA device pointers on the handle's device, *_host are host pointers.  All launches are ordered on
+ * the `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream).  One handle per
+ * device; a handle may be used by one host thread at a time.  The library allocates its weights, static
+ * tables and activation workspace with cudaMalloc at finalize / first use of a batch size and frees them in
+ * selftok_destroy; it never touches caller buffers other than the documented outputs.
+ */
+#ifndef SELFTOK_B200_H_
+#define SELFTOK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct selftok_engine* selftok_handle_t;
+
+typedef enum selftok_status {
+  SELFTOK_OK = 0,
+  SELFTOK_ERR_BAD_ARG = -1,       /* null pointer, bad shape, batch <= 0 ...                       */
+  SELFTOK_ERR_UNSUPPORTED = -2,   /* configuration outside what the kernels implement              */
+  SELFTOK_ERR_STATE = -3,         /* call order violated (e.g. decode before finalize)             */
+  SELFTOK_ERR_MISSING_TENSOR = -4,/* finalize: a checkpoint key the path needs was never loaded    */
+  SELFTOK_ERR_CUDA = -5,          /* a CUDA runtime / driver call failed; see selftok_last_error() */
+  SELFTOK_ERR_NO_DEVICE = -6      /* no sm_100 device visible — there is no CPU fallback            */
+} selftok_status;
+
+/* GEMM arithmetic of the decoder (MMDiT / renderer).  The encoder and VQ always run fp32 FFMA (token ids must
+ * be bit-stable; SURVEY 7 hard part 2). */
+typedef enum selftok_precision {
+  SELFTOK_PREC_FP32_SIMT = 0,     /* fp32 FFMA GEMMs + fp32 attention (bring-up / bisecting reference)       */
+  SELFTOK_PREC_BF16X3 = 1,        /* tcgen05 kind::f16: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate   */
+  SELFTOK_PREC_BF16 = 2           /* tcgen05 kind::f16 single pass (bf16 operands, fp32 accumulate)          */
+} selftok_precision;
+
+/* Flat view of cfg.tokenizer.params (configs/res256/256-eval.yml:48-105) after the reference's registries
+ * (model_zoo.py:22-60,177-180) are resolved.  Mirrors selftoktokenizer_b200/config.py:SelftokDims. */
+typedef struct selftok_config_t {
+  int32_t K;                /* tokens per image (k: 512)                                        */
+  int32_t latent;           /* latent side = image_size / 8 (32)                                */
+  int32_t in_channels;      /* 16                                                               */
+  int32_t enc_patch, enc_hidden, enc_heads, enc_depth, enc_qdim, enc_qheads, enc_pos_max;
+  int32_t codebook_size, code_dim;
+  int32_t dit_depth;        /* hidden = 64*depth, heads = depth (sd3/mmdit.py:708-709)          */
+  int32_t dit_patch, dit_pos_max;
+  int32_t renderer;         /* 0: MMDiT (50-step decode)   1: MMDiT_Renderer (one pass)        */
+  int32_t context_see_xt;   /* 256-eval.yml:88                                                   */
+  int32_t precision;        /* selftok_precision                                                 */
+  int32_t device;           /* CUDA device ordinal                                               */
+} selftok_config_t;
+
+enum { SELFTOK_F32 = 0, SELFTOK_I64 = 1 };
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+int selftok_create(const selftok_config_t* cfg, selftok_handle_t* out);
+int selftok_destroy(selftok_handle_t h);
+const char* selftok_last_error(void);
+/* ABI / build identification: "selftok_b200 <abi> sm_100a <build flags>" */
+const char* selftok_version(void);
+
+/* ---- weights: one call per checkpoint key, names exactly as in the reference state dict ------------------
+ * ("encoder.blocks.3.attn.qkv.weight", "model.joint_blocks.7.x_block.mlp.fc1.bias", ...).
+ * `data` may be a host or a device pointer (is_device); fp32 only.  Unknown names are accepted and ignored at
+ * finalize (the reference loads with strict=False). */
+int selftok_load_tensor(selftok_handle_t h, const char* name, const void* data, int dtype,
+                        int ndim, const int64_t* shape, int is_device);
+
+/* ---- static sampler tables (host pointers), evaluated by the caller with the reference's own torch
+ * expressions (selftoktokenizer_b200/schedule.py):  t/dt [steps] fp32, k [steps] int32 (last visible context
+ * index), t_freq [steps,256] sinusoidal features of 1000*t_i, pos_freq [K,256] features of 1000+8k. */
+int selftok_set_schedule(selftok_handle_t h, int steps, const float* t_host, const float* dt_host,
+                         const int32_t* k_host, const float* t_freq_host, const float* pos_freq_host);
+
+/* Packs weights (bf16 hi/lo planes for the tensor-core GEMMs), builds every input-independent table
+ * (encoder adaLN [depth,K,6Q]; decoder context adaLN [L-1,K,6D]; per-step x adaLN [L,steps,6D]; cropped
+ * positional embeddings) on the device, and frees staging copies. */
+int selftok_finalize(selftok_handle_t h, void* stream);
+
+/* ---- hot path, device buffers ---------------------------------------------------------------------------- */
+/* x0_dev [B,C,latent,latent] fp32 (VAE latent after SD3LatentFormat.process_in) -> tokens_dev [B,K] int64,
+ * outs_q_dev [B,K,code_dim] fp32 (may be NULL), feats_dev [B,K,enc_qdim] fp32 pre-VQ features (may be NULL). */
+int selftok_encode(selftok_handle_t h, const float* x0_dev, int B, int64_t* tokens_dev, float* outs_q_dev,
+                   float* feats_dev, void* stream);
+/* Standalone fused VQ: z_dev [R,enc_qdim] fp32 -> ids_dev [R] int64, outs_q_dev [R,code_dim] (may be NULL). */
+int selftok_vq_argmax(selftok_handle_t h, const float* z_dev, int64_t R, int64_t* ids_dev, float* outs_q_dev,
+                      void* stream);
+/* tokens_dev [B,K] int64 -> outs_q_dev [B,K,code_dim] fp32 (codebook gather + final_layer_norm3). */
+int selftok_lookup(selftok_handle_t h, const int64_t* tokens_dev, int B, float* outs_q_dev, void* stream);
+/* tokens_dev [B,K], noise_dev [B,C,latent,latent] fp32 -> x0_out_dev (same shape): `steps` Euler steps of the
+ * rectified flow (steps <= the schedule's; the loop is captured in one CUDA graph per batch size).
+ * x0_out_dev may alias noise_dev. */
+int selftok_decode(selftok_handle_t h, const int64_t* tokens_dev, const float* noise_dev, int B, int steps,
+                   float* x0_out_dev, void* stream);
+/* One MMDiT velocity evaluation at schedule index `step` on latents x_dev (testing / bisecting entry). */
+int selftok_dit_velocity(selftok_handle_t h, const int64_t* tokens_dev, const float* x_dev, int B, int step,
+                         float* v_out_dev, void* stream);
+/* renderer handles only: tokens_dev [B,K] -> pred_x0 [B,C,latent,latent]. */
+int selftok_render(selftok_handle_t h, const int64_t* tokens_dev, int B, float* x0_out_dev, void* stream);
+
+/* ---- hot path, host buffers (what SelftokPipeline's numpy-in / tensor-out API maps to; H2D and D2H copies are
+ * inside the call, on `stream`, followed by a stream synchronize) --------------------------------------------- */
+int selftok_encode_host(selftok_handle_t h, const float* x0_host, int B, int64_t* tokens_host, void* stream);
+int selftok_decode_host(selftok_handle_t h, const int64_t* tokens_host, const float* noise_host, int B, int steps,
+                        float* x0_out_host, void* stream);
+int selftok_render_host(selftok_handle_t h, const int64_t* tokens_host, int B, float* x0_out_host, void* stream);
+
+/* ---- introspection ----------------------------------------------------------------------------------------- */
+/* Number of kernel launches issued (or replayed from a graph) by the last hot-path call on this handle. */
+int64_t selftok_last_launch_count(selftok_handle_t h);
+/* Device bytes currently held by the handle (weights + tables + workspaces). */
+int64_t selftok_device_bytes(selftok_handle_t h);
+/* Enable (1) / disable (0) CUDA-graph capture of the decode loop (default 1). */
+int selftok_set_use_graph(selftok_handle_t h, int enable);
+
+/* ---- kernel-level entry points (parity tests and micro-benchmarks call these through the same ABI) ---------- */
+/* y[M,N] = act(A[M,K] W[N,K]^T + bias) (+ epilogue), fp32 FFMA.  act: 0 none, 1 gelu-tanh, 2 silu. */
+int selftok_k_linear_f32(const float* A_dev, const float* W_dev, const float* bias_dev, float* out_dev,
+                         int64_t M, int N, int K, int act, void* stream);
+/* Same product on the tcgen05 path: A/W given as fp32, split into bf16 planes internally (nsplit 1 or 3). */
+int selftok_k_linear_tc(const float* A_dev, const float* W_dev, const float* bias_dev, float* out_dev,
+                        int64_t M, int N, int K, int nsplit, void* stream);
+/* out = LN(x) * (1 + scale[m % period]) + shift[m % period], rows of D; eps 1e-6, no affine. */
+int selftok_k_ln_mod_f32(const float* x_dev, const float* shift_dev, const float* scale_dev, int64_t ld_mod,
+                         int period, float* out_dev, int64_t M, int D, void* stream);
+/* softmax(Q K^T / sqrt(hd)) V, fp32; q [B,Sq,H*hd], k/v two concatenated segments [B,S1,H*hd] + [B,S2,H*hd]
+ * (S2 may be 0), each with its own row stride in floats. */
+int selftok_k_attention_f32(const float* q_dev, int64_t q_ld, const float* k1_dev, const float* v1_dev, int64_t kv1_ld,
+                            int S1, const float* k2_dev, const float* v2_dev, int64_t kv2_ld, int S2,
+                            float* out_dev, int64_t out_ld, int B, int Sq, int H, int hd, void* stream);
+/* Tensor-core (bf16x3 / bf16) attention over a packed qkv buffer [B,S,3,H,64]; ctx_rows = number of leading rows
+ * whose queries may only see the first `ctx_keys` keys (renderer rule; pass 0 for plain dense attention). */
+int selftok_k_attention_tc(const float* qkv_dev, float* out_dev, int B, int S, int H, int nsplit,
+                           int ctx_rows, int ctx_keys, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SELFTOK_B200_H_ */

@@ -1,0 +1,318 @@
+"""ctypes binding of include/selftok_b200.h (libselftok_b200.so) — the only way Python reaches the kernels.
+
+There is deliberately no fallback: if the library is missing or no sm_100 GPU is visible, construction raises
+(`SelftokError`).  PyTorch appears here only as the owner of device memory (`tensor.data_ptr()`) and of the
+current stream handle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import schedule as sched
+from .config import SelftokDims
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libselftok_b200.so")
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+# every symbol include/selftok_b200.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "selftok_create", "selftok_destroy", "selftok_last_error", "selftok_version", "selftok_load_tensor",
+    "selftok_set_schedule", "selftok_finalize", "selftok_encode", "selftok_vq_argmax", "selftok_lookup",
+    "selftok_decode", "selftok_dit_velocity", "selftok_render", "selftok_encode_host", "selftok_decode_host",
+    "selftok_render_host", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
+    "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
+    "selftok_k_attention_tc",
+]
+
+
+class SelftokError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "K", "latent", "in_channels", "enc_patch", "enc_hidden", "enc_heads", "enc_depth", "enc_qdim", "enc_qheads",
+        "enc_pos_max", "codebook_size", "code_dim", "dit_depth", "dit_patch", "dit_pos_max", "renderer",
+        "context_see_xt", "precision", "device")]
+
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None) -> C.CDLL:
+    """dlopen the CUDA library.  Raises if it has not been built (python -m selftoktokenizer_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("SELFTOK_B200_LIB", _LIB_PATH)
+    if not os.path.exists(path):
+        raise SelftokError(f"{path} not found: build it with `python -m selftoktokenizer_b200.build` "
+                           "(selftok_b200 has no CPU / PyTorch fallback)")
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.selftok_last_error.restype = C.c_char_p
+    lib.selftok_version.restype = C.c_char_p
+    lib.selftok_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    lib.selftok_destroy.argtypes = [vp]
+    lib.selftok_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, i32, C.POINTER(i64), i32]
+    lib.selftok_set_schedule.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    lib.selftok_finalize.argtypes = [vp, vp]
+    lib.selftok_encode.argtypes = [vp, vp, i32, vp, vp, vp, vp]
+    lib.selftok_vq_argmax.argtypes = [vp, vp, i64, vp, vp, vp]
+    lib.selftok_lookup.argtypes = [vp, vp, i32, vp, vp]
+    lib.selftok_decode.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.selftok_dit_velocity.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.selftok_render.argtypes = [vp, vp, i32, vp, vp]
+    lib.selftok_encode_host.argtypes = [vp, vp, i32, vp, vp]
+    lib.selftok_decode_host.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.selftok_render_host.argtypes = [vp, vp, i32, vp, vp]
+    lib.selftok_last_launch_count.argtypes = [vp]
+    lib.selftok_last_launch_count.restype = i64
+    lib.selftok_device_bytes.argtypes = [vp]
+    lib.selftok_device_bytes.restype = i64
+    lib.selftok_set_use_graph.argtypes = [vp, i32]
+    lib.selftok_k_linear_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.selftok_k_linear_tc.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.selftok_k_ln_mod_f32.argtypes = [vp, vp, vp, i64, i32, vp, i64, i32, vp]
+    lib.selftok_k_attention_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, i64, i32, vp, i64, i32, i32, i32, i32, vp]
+    lib.selftok_k_attention_tc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    for name in SYMBOLS:
+        getattr(lib, name)          # AttributeError here == header / library drift
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load_library().selftok_last_error()
+        raise SelftokError(f"selftok_b200 status {status}: {msg.decode() if msg else '?'}")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One handle (`selftok_handle_t`) on one device: weights, static tables, workspaces, CUDA graphs."""
+
+    def __init__(self, dims: SelftokDims, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "bf16x3",
+                 steps: int = 50, start: float = 1.0):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise SelftokError("no CUDA device: selftok_b200 has no CPU fallback")
+        self.dims = dims
+        self.device = torch.device(device)
+        self.precision = precision
+        dims.validate()
+        cfg = _Config(K=dims.K, latent=dims.latent, in_channels=dims.in_channels, enc_patch=dims.enc_patch,
+                      enc_hidden=dims.enc_hidden, enc_heads=dims.enc_heads, enc_depth=dims.enc_depth,
+                      enc_qdim=dims.enc_qdim, enc_qheads=dims.enc_qheads, enc_pos_max=dims.enc_pos_max,
+                      codebook_size=dims.codebook_size, code_dim=dims.code_dim, dit_depth=dims.dit_depth,
+                      dit_patch=dims.dit_patch, dit_pos_max=dims.dit_pos_max, renderer=int(dims.renderer),
+                      context_see_xt=int(dims.context_see_xt), precision=PREC[precision],
+                      device=self.device.index or 0)
+        h = C.c_void_p()
+        check(self.lib.selftok_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        try:
+            self._load(state_dict)
+            if dims.renderer:
+                # MMDiT_Renderer: one pass at t = 1000 with all K tokens visible (sd3/mmdit.py:1523)
+                tb = sched.make_tables(dims.K, dims.stages, dims.k_per_stage, 1)
+                self.steps = 1
+                t_freq = sched.renderer_t_freq()
+                k = np.full(1, dims.K - 1, dtype=np.int32)
+            else:
+                tb = sched.make_tables(dims.K, dims.stages, dims.k_per_stage, steps, start)
+                self.steps = steps
+                t_freq = tb.t_freq
+                k = tb.k.numpy().astype(np.int32)
+            self.tables = tb
+            t = np.ascontiguousarray(tb.t.numpy(), dtype=np.float32)
+            dt = np.ascontiguousarray(tb.dt.numpy(), dtype=np.float32)
+            tf = np.ascontiguousarray(t_freq.numpy(), dtype=np.float32)
+            pf = np.ascontiguousarray(tb.pos_freq.numpy(), dtype=np.float32)
+            check(self.lib.selftok_set_schedule(self.h, self.steps, t.ctypes.data, dt.ctypes.data, k.ctypes.data,
+                                                tf.ctypes.data, pf.ctypes.data))
+            with torch.cuda.device(self.device):
+                check(self.lib.selftok_finalize(self.h, _stream_ptr(self.device)))
+        except Exception:
+            self.close()
+            raise
+
+    def _load(self, sd: Dict[str, torch.Tensor]) -> None:
+        for name, t in sd.items():
+            if not torch.is_tensor(t) or not t.is_floating_point() or t.numel() == 0:
+                continue
+            if not (name.startswith("encoder.") or name.startswith("model.")):
+                continue
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(torch.float32).contiguous()
+            shape = (C.c_int64 * max(t.dim(), 1))(*t.shape)
+            is_dev = int(t.is_cuda)
+            if is_dev and t.device != self.device:
+                t = t.to(self.device)
+            check(self.lib.selftok_load_tensor(self.h, name.encode(), t.data_ptr(), 0, t.dim(), shape, is_dev))
+
+    # ------------------------------------------------------------------ hot path (device tensors)
+    def _dev(self, t: torch.Tensor, dtype) -> torch.Tensor:
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def encode(self, x0: torch.Tensor, return_aux: bool = False):
+        """x0 [B,C,h,w] fp32 latents -> tokens [B,K] int64 (device)."""
+        d = self.dims
+        x0 = self._dev(x0, torch.float32)
+        B = x0.shape[0]
+        tokens = torch.empty(B, d.K, dtype=torch.int64, device=self.device)
+        outs_q = torch.empty(B, d.K, d.code_dim, dtype=torch.float32, device=self.device) if return_aux else None
+        feats = torch.empty(B, d.K, d.enc_qdim, dtype=torch.float32, device=self.device) if return_aux else None
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_encode(self.h, x0.data_ptr(), B, tokens.data_ptr(), _ptr(outs_q), _ptr(feats),
+                                          _stream_ptr(self.device)))
+        return (tokens, outs_q, feats) if return_aux else tokens
+
+    def vq_argmax(self, z: torch.Tensor, with_outs_q: bool = True):
+        z = self._dev(z, torch.float32)
+        R = z.numel() // self.dims.enc_qdim
+        ids = torch.empty(R, dtype=torch.int64, device=self.device)
+        outs_q = torch.empty(R, self.dims.code_dim, dtype=torch.float32, device=self.device) if with_outs_q else None
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_vq_argmax(self.h, z.data_ptr(), R, ids.data_ptr(), _ptr(outs_q), _stream_ptr(self.device)))
+        return ids, outs_q
+
+    def lookup(self, tokens: torch.Tensor) -> torch.Tensor:
+        tokens = self._dev(tokens, torch.int64)
+        B = tokens.shape[0]
+        out = torch.empty(B, self.dims.K, self.dims.code_dim, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_lookup(self.h, tokens.data_ptr(), B, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def decode(self, tokens: torch.Tensor, noise: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
+        tokens = self._dev(tokens, torch.int64)
+        noise = self._dev(noise, torch.float32)
+        B = tokens.shape[0]
+        out = torch.empty_like(noise)
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_decode(self.h, tokens.data_ptr(), noise.data_ptr(), B, steps or self.steps,
+                                          out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def dit_velocity(self, tokens: torch.Tensor, x: torch.Tensor, step: int) -> torch.Tensor:
+        tokens = self._dev(tokens, torch.int64)
+        x = self._dev(x, torch.float32)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_dit_velocity(self.h, tokens.data_ptr(), x.data_ptr(), tokens.shape[0], step,
+                                                out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def render(self, tokens: torch.Tensor) -> torch.Tensor:
+        tokens = self._dev(tokens, torch.int64)
+        d = self.dims
+        out = torch.empty(tokens.shape[0], d.in_channels, d.latent, d.latent, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_render(self.h, tokens.data_ptr(), tokens.shape[0], out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # ------------------------------------------------------------------ hot path (host buffers; copies inside the call)
+    def encode_host(self, x0: torch.Tensor, tokens_out: torch.Tensor) -> torch.Tensor:
+        assert not x0.is_cuda and not tokens_out.is_cuda and x0.dtype == torch.float32 and tokens_out.dtype == torch.int64
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_encode_host(self.h, x0.data_ptr(), x0.shape[0], tokens_out.data_ptr(), _stream_ptr(self.device)))
+        return tokens_out
+
+    def decode_host(self, tokens: torch.Tensor, noise: torch.Tensor, out: torch.Tensor, steps: Optional[int] = None) -> torch.Tensor:
+        assert not tokens.is_cuda and not noise.is_cuda and not out.is_cuda
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_decode_host(self.h, tokens.data_ptr(), noise.data_ptr(), tokens.shape[0],
+                                               steps or self.steps, out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def render_host(self, tokens: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        assert not tokens.is_cuda and not out.is_cuda
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_render_host(self.h, tokens.data_ptr(), tokens.shape[0], out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    # ------------------------------------------------------------------ misc
+    def set_use_graph(self, enable: bool) -> None:
+        check(self.lib.selftok_set_use_graph(self.h, int(enable)))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self.lib.selftok_last_launch_count(self.h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.selftok_device_bytes(self.h))
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.selftok_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- kernel-level helpers used by tests and micro-benchmarks ---------------------------------------------------
+def k_linear_f32(A, W, bias=None, act=0):
+    lib = load_library()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    check(lib.selftok_k_linear_f32(A.data_ptr(), W.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, act, _stream_ptr(A.device)))
+    return out
+
+
+def k_linear_tc(A, W, bias=None, nsplit=3):
+    lib = load_library()
+    M, K = A.shape
+    N = W.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    check(lib.selftok_k_linear_tc(A.data_ptr(), W.data_ptr(), _ptr(bias), out.data_ptr(), M, N, K, nsplit, _stream_ptr(A.device)))
+    return out
+
+
+def k_ln_mod_f32(x, shift=None, scale=None, period=1):
+    lib = load_library()
+    M, D = x.shape
+    out = torch.empty_like(x)
+    ld = shift.shape[-1] if shift is not None else 0
+    check(lib.selftok_k_ln_mod_f32(x.data_ptr(), _ptr(shift), _ptr(scale), ld, period, out.data_ptr(), M, D, _stream_ptr(x.device)))
+    return out
+
+
+def k_attention_f32(q, k1, v1, k2=None, v2=None, heads=1):
+    """q [B,Sq,H*hd], k1/v1 [B,S1,H*hd], optional second key/value segment."""
+    lib = load_library()
+    B, Sq, Dm = q.shape
+    S1 = k1.shape[1]
+    S2 = 0 if k2 is None else k2.shape[1]
+    out = torch.empty_like(q)
+    check(lib.selftok_k_attention_f32(q.data_ptr(), Dm, k1.data_ptr(), v1.data_ptr(), Dm, S1, _ptr(k2), _ptr(v2), Dm, S2,
+                                      out.data_ptr(), Dm, B, Sq, heads, Dm // heads, _stream_ptr(q.device)))
+    return out
+
+
+def k_attention_tc(qkv, heads, nsplit=3, ctx_rows=0, ctx_keys=0):
+    """qkv [B,S,3,H,64] fp32 -> [B,S,H*64]."""
+    lib = load_library()
+    B, S = qkv.shape[0], qkv.shape[1]
+    out = torch.empty(B, S, heads * 64, dtype=torch.float32, device=qkv.device)
+    check(lib.selftok_k_attention_tc(qkv.data_ptr(), out.data_ptr(), B, S, heads, nsplit, ctx_rows, ctx_keys, _stream_ptr(qkv.device)))
+    return out

@@ -1,0 +1,74 @@
+// Shared host/device helpers for the selftok_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace stk {
+
+// ---- host-side error plumbing (status codes mirror include/selftok_b200.h) ---------------------------------
+void set_error(const std::string& msg);
+#define STK_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) {                                                                      \
+      ::stk::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                       std::to_string(__LINE__));                                                 \
+      return -5;                                                                                  \
+    }                                                                                             \
+  } while (0)
+#define STK_CHECK(cond, code, msg)                                                                \
+  do {                                                                                            \
+    if (!(cond)) {                                                                                \
+      ::stk::set_error(std::string(msg) + " [" #cond "] @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+      return (code);                                                                              \
+    }                                                                                             \
+  } while (0)
+#define STK_TRY(expr)                                                                             \
+  do {                                                                                            \
+    int _s = (expr);                                                                              \
+    if (_s != 0) return _s;                                                                       \
+  } while (0)
+
+extern thread_local int64_t g_launch_count;   // bumped by every launch wrapper
+inline void count_launch() { ++g_launch_count; }
+
+// ---- device helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// torch.nn.GELU(approximate="tanh"): 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float inner = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.0f + tanhf(inner));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_GELU) return gelu_tanh(x);
+  if (act == ACT_SILU) return silu(x);
+  return x;
+}
+
+// bf16 split: hi = rn(x), lo = rn(x - hi).  hi + lo carries ~16 mantissa bits of x.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+}  // namespace stk

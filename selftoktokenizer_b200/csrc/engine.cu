@@ -1,0 +1,841 @@
+// selftok_b200 engine: the C ABI of include/selftok_b200.h.
+//
+// Host-side orchestration of the encode / decode hot path of mimogpt/infer/SelftokPipeline.py — weights under the
+// reference's checkpoint key names, every input-independent table built once at finalize, one workspace per batch
+// size, and the 50-step sampler captured in one CUDA graph.  All arithmetic is in the kernels of kernels_simt.cu
+// (fp32 FFMA: encoder, VQ, tables), gemm_tc.cu (tcgen05 GEMMs of the MMDiT) and attn_tc.cu (joint attention).
+#include "../../include/selftok_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace stk {
+static thread_local std::string g_error;
+thread_local int64_t g_launch_count = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace stk
+
+using namespace stk;
+typedef __nv_bfloat16 bf16;
+
+struct Tensor {
+  float* d = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel = 0;
+};
+struct WPack {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+};
+
+struct DecodeWs {       // activation workspace of the MMDiT for one batch size
+  int B = 0;
+  int64_t* tokens = nullptr;
+  float *outs_q = nullptr, *x_lat = nullptr, *patch = nullptr, *ctx0 = nullptr, *ctx = nullptr, *x = nullptr;
+  float *qkv = nullptr, *o_final = nullptr;
+  // fp32 mode activations
+  float *a_c = nullptr, *a_x = nullptr, *attn_c = nullptr, *attn_x = nullptr, *h_c = nullptr, *h_x = nullptr;
+  // tensor-core mode activations (bf16 planes)
+  bf16 *a_c_hi = nullptr, *a_c_lo = nullptr, *a_x_hi = nullptr, *a_x_lo = nullptr;
+  bf16 *attn_c_hi = nullptr, *attn_c_lo = nullptr, *attn_x_hi = nullptr, *attn_x_lo = nullptr;
+  bf16 *h_c_hi = nullptr, *h_c_lo = nullptr, *h_x_hi = nullptr, *h_x_lo = nullptr;
+  std::vector<void*> allocs;
+};
+struct EncodeWs {
+  int B = 0;
+  float *x0 = nullptr, *patch = nullptr, *x = nullptr, *q = nullptr, *xn = nullptr, *qn = nullptr, *xqkv = nullptr,
+        *xkv = nullptr, *qqkv = nullptr, *xattn = nullptr, *qattn = nullptr, *xh = nullptr, *qh = nullptr, *outs_q = nullptr;
+  int64_t* tokens = nullptr;
+  std::vector<void*> allocs;
+};
+
+struct selftok_engine {
+  selftok_config_t cfg;
+  int D = 0, H = 0, Nimg = 0, Nenc = 0;
+  bool finalized = false;
+  bool use_graph = true;
+  std::unordered_map<std::string, Tensor> w;
+  std::unordered_map<std::string, WPack> wp;
+  std::vector<void*> allocs;            // tables + packed weights
+  int64_t bytes = 0;
+  // schedule
+  int steps = 0;
+  std::vector<float> t, dt;
+  std::vector<int> k;
+  float *t_freq = nullptr, *pos_freq = nullptr;
+  // tables
+  float *enc_mod = nullptr, *enc_pos = nullptr, *cbt = nullptr;
+  float *ctx_mod = nullptr, *x_mod = nullptr, *ctx_last_mod = nullptr, *final_mod = nullptr, *dit_pos = nullptr;
+  float* rend_x0 = nullptr;
+  DecodeWs dws;
+  EncodeWs ews;
+  std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (B, steps) -> (exec, launches)
+  int64_t last_launches = 0;
+};
+
+static int dmalloc(selftok_engine* e, std::vector<void*>& pool, void** p, size_t bytes) {
+  STK_CUDA(cudaMalloc(p, bytes ? bytes : 16));
+  pool.push_back(*p);
+  e->bytes += (int64_t)bytes;
+  return 0;
+}
+template <typename T>
+static int dalloc(selftok_engine* e, std::vector<void*>& pool, T** p, int64_t n) {
+  return dmalloc(e, pool, reinterpret_cast<void**>(p), sizeof(T) * (size_t)n);
+}
+static void free_pool(selftok_engine* e, std::vector<void*>& pool) {
+  for (void* p : pool) cudaFree(p);
+  pool.clear();
+}
+
+static const Tensor* find(selftok_engine* e, const std::string& name) {
+  auto it = e->w.find(name);
+  return it == e->w.end() ? nullptr : &it->second;
+}
+#define GETW(var, name)                                                             \
+  const Tensor* var = find(e, (name));                                              \
+  if (!var) {                                                                       \
+    set_error(std::string("checkpoint key not loaded: ") + (name));                 \
+    return SELFTOK_ERR_MISSING_TENSOR;                                              \
+  }
+
+static bool tc_mode(const selftok_engine* e) { return e->cfg.precision != SELFTOK_PREC_FP32_SIMT; }
+static int nsplit(const selftok_engine* e) { return e->cfg.precision == SELFTOK_PREC_BF16X3 ? 3 : 1; }
+
+// y = act(A W^T + b) with weights looked up by checkpoint prefix (fp32 FFMA path)
+static int lin32(selftok_engine* e, const std::string& prefix, const float* A, int64_t lda, int64_t M, Epilogue ep,
+                 cudaStream_t s) {
+  GETW(W, prefix + ".weight");
+  GETW(Bv, prefix + ".bias");
+  int N = (int)W->shape[0];
+  int K = (int)(W->numel / W->shape[0]);
+  ep.bias = Bv->d;
+  if (ep.ldo == 0) ep.ldo = N;
+  return launch_linear_f32(A, lda, W->d, K, M, N, K, ep, s);
+}
+// tcgen05 path: A given as bf16 planes
+static int lintc(selftok_engine* e, const std::string& prefix, const bf16* A_hi, const bf16* A_lo, int64_t M,
+                 Epilogue ep, cudaStream_t s) {
+  GETW(W, prefix + ".weight");
+  GETW(Bv, prefix + ".bias");
+  auto it = e->wp.find(prefix + ".weight");
+  STK_CHECK(it != e->wp.end(), SELFTOK_ERR_STATE, "packed weight missing");
+  int N = (int)W->shape[0];
+  int K = (int)(W->numel / W->shape[0]);
+  ep.bias = Bv->d;
+  if (ep.ldo == 0) ep.ldo = N;
+  return launch_gemm_tc(A_hi, A_lo, it->second.hi, it->second.lo, M, N, K, nsplit(e), ep, s);
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI: lifetime
+extern "C" __attribute__((visibility("default"))) const char* selftok_last_error(void) { return g_error.c_str(); }
+extern "C" __attribute__((visibility("default"))) const char* selftok_version(void) { return "selftok_b200 abi1 sm_100a (fp32-ffma + tcgen05 kind::f16)"; }
+
+extern "C" __attribute__((visibility("default"))) int selftok_create(const selftok_config_t* cfg, selftok_handle_t* out) {
+  STK_CHECK(cfg && out, SELFTOK_ERR_BAD_ARG, "selftok_create: null argument");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) {
+    set_error("no CUDA device visible: selftok_b200 has no CPU fallback");
+    return SELFTOK_ERR_NO_DEVICE;
+  }
+  STK_CHECK(cfg->device >= 0 && cfg->device < ndev, SELFTOK_ERR_BAD_ARG, "bad device ordinal");
+  cudaDeviceProp prop;
+  STK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_error("device is not sm_100 (Blackwell B200): kernels are built for sm_100a only");
+    return SELFTOK_ERR_NO_DEVICE;
+  }
+  STK_CHECK(cfg->K > 0 && cfg->latent > 0 && cfg->dit_depth > 0 && cfg->enc_depth > 0, SELFTOK_ERR_BAD_ARG, "bad dims");
+  STK_CHECK(cfg->code_dim == 16, SELFTOK_ERR_UNSUPPORTED, "code_dim must be 16");
+  STK_CHECK(cfg->enc_hidden % cfg->enc_heads == 0 && cfg->enc_qdim % cfg->enc_qheads == 0, SELFTOK_ERR_BAD_ARG, "bad heads");
+  int hd1 = cfg->enc_hidden / cfg->enc_heads, hd2 = cfg->enc_qdim / cfg->enc_qheads;
+  STK_CHECK((hd1 == 16 || hd1 == 32 || hd1 == 64) && (hd2 == 16 || hd2 == 32 || hd2 == 64), SELFTOK_ERR_UNSUPPORTED,
+            "encoder head_dim must be 16/32/64");
+  STK_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SELFTOK_ERR_BAD_ARG, "bad precision");
+  STK_CUDA(cudaSetDevice(cfg->device));
+  selftok_engine* e = new selftok_engine();
+  e->cfg = *cfg;
+  e->D = 64 * cfg->dit_depth;
+  e->H = cfg->dit_depth;
+  e->Nimg = (cfg->latent / cfg->dit_patch) * (cfg->latent / cfg->dit_patch);
+  e->Nenc = (cfg->latent / cfg->enc_patch) * (cfg->latent / cfg->enc_patch);
+  if (tc_mode(e)) {
+    int st = gemm_tc_init();
+    if (st != 0) { delete e; return st; }
+  }
+  *out = e;
+  return SELFTOK_OK;
+}
+
+static void free_dws(selftok_engine* e) { free_pool(e, e->dws.allocs); e->dws = DecodeWs(); }
+static void free_ews(selftok_engine* e) { free_pool(e, e->ews.allocs); e->ews = EncodeWs(); }
+
+extern "C" __attribute__((visibility("default"))) int selftok_destroy(selftok_handle_t e) {
+  if (!e) return SELFTOK_OK;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);
+  for (auto& kv : e->w) cudaFree(kv.second.d);
+  free_pool(e, e->allocs);
+  free_dws(e);
+  free_ews(e);
+  delete e;
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_load_tensor(selftok_handle_t e, const char* name, const void* data, int dtype, int ndim,
+                                   const int64_t* shape, int is_device) {
+  STK_CHECK(e && name && data && shape && ndim >= 0 && ndim <= 8, SELFTOK_ERR_BAD_ARG, "selftok_load_tensor: bad argument");
+  STK_CHECK(dtype == SELFTOK_F32, SELFTOK_ERR_UNSUPPORTED, "only fp32 checkpoint tensors are supported");
+  STK_CHECK(!e->finalized, SELFTOK_ERR_STATE, "load_tensor after finalize");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  Tensor t;
+  t.numel = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); t.numel *= shape[i]; }
+  STK_CHECK(t.numel > 0, SELFTOK_ERR_BAD_ARG, "empty tensor");
+  auto it = e->w.find(name);
+  if (it != e->w.end()) { cudaFree(it->second.d); e->bytes -= it->second.numel * 4; e->w.erase(it); }
+  STK_CUDA(cudaMalloc(&t.d, sizeof(float) * (size_t)t.numel));
+  e->bytes += t.numel * 4;
+  STK_CUDA(cudaMemcpy(t.d, data, sizeof(float) * (size_t)t.numel, is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  e->w[name] = t;
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_set_schedule(selftok_handle_t e, int steps, const float* t_host, const float* dt_host,
+                                    const int32_t* k_host, const float* t_freq_host, const float* pos_freq_host) {
+  STK_CHECK(e && steps > 0 && t_host && dt_host && k_host && t_freq_host && pos_freq_host, SELFTOK_ERR_BAD_ARG,
+            "selftok_set_schedule: bad argument");
+  STK_CHECK(!e->finalized, SELFTOK_ERR_STATE, "set_schedule after finalize");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  e->steps = steps;
+  e->t.assign(t_host, t_host + steps);
+  e->dt.assign(dt_host, dt_host + steps);
+  e->k.assign(k_host, k_host + steps);
+  for (int i = 0; i < steps; ++i)
+    STK_CHECK(e->k[i] >= 0 && e->k[i] < e->cfg.K, SELFTOK_ERR_BAD_ARG, "schedule k out of range");
+  STK_TRY(dalloc(e, e->allocs, &e->t_freq, (int64_t)steps * 256));
+  STK_TRY(dalloc(e, e->allocs, &e->pos_freq, (int64_t)e->cfg.K * 256));
+  STK_CUDA(cudaMemcpy(e->t_freq, t_freq_host, sizeof(float) * steps * 256, cudaMemcpyHostToDevice));
+  STK_CUDA(cudaMemcpy(e->pos_freq, pos_freq_host, sizeof(float) * e->cfg.K * 256, cudaMemcpyHostToDevice));
+  return SELFTOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ finalize
+// adaLN table of a position-indexed block:  Linear(SiLU(t_embedder(pos_freq)))  (modules.py:311-318; mmdit.py:446-458)
+static int build_pos_table(selftok_engine* e, const std::string& blk, const float* freq, int rows, float* tmp1, float* tmp2,
+                           float* out, cudaStream_t s) {
+  Epilogue ep;
+  ep.act = ACT_SILU; ep.out = tmp1;
+  STK_TRY(lin32(e, blk + "t_embedder.mlp.0", freq, 256, rows, ep, s));
+  GETW(W2, blk + "t_embedder.mlp.2.weight");
+  int dim = (int)W2->shape[0];
+  ep.out = tmp2;                                            // SiLU applied here: t_emb is only consumed through SiLU
+  STK_TRY(lin32(e, blk + "t_embedder.mlp.2", tmp1, dim, rows, ep, s));
+  Epilogue ep2;
+  ep2.out = out;
+  STK_TRY(lin32(e, blk + "adaLN_modulation.1", tmp2, dim, rows, ep2, s));
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_handle_t e, void* stream) {
+  STK_CHECK(e, SELFTOK_ERR_BAD_ARG, "null handle");
+  STK_CHECK(!e->finalized, SELFTOK_ERR_STATE, "already finalized");
+  STK_CHECK(e->steps > 0, SELFTOK_ERR_STATE, "selftok_set_schedule must precede finalize");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const selftok_config_t& c = e->cfg;
+  const int K = c.K, Q = c.enc_qdim, D = e->D, L = c.dit_depth, T = e->steps;
+  // scratch for the table MLPs
+  float *tmp1, *tmp2;
+  int64_t rows_max = K > T ? K : T, dim_max = D > Q ? D : Q;
+  std::vector<void*> scratch;
+  STK_TRY(dalloc(e, scratch, &tmp1, rows_max * dim_max));
+  STK_TRY(dalloc(e, scratch, &tmp2, rows_max * dim_max));
+  // ---- encoder: adaLN tables [depth][K][6Q], cropped positional grid, transposed codebook
+  STK_TRY(dalloc(e, e->allocs, &e->enc_mod, (int64_t)c.enc_depth * K * 6 * Q));
+  for (int i = 0; i < c.enc_depth; ++i)
+    STK_TRY(build_pos_table(e, "encoder.blocks." + std::to_string(i) + ".", e->pos_freq, K, tmp1, tmp2,
+                            e->enc_mod + (int64_t)i * K * 6 * Q, s));
+  {
+    GETW(pe, "encoder.pos_embed");
+    STK_CHECK(pe->numel == (int64_t)c.enc_pos_max * c.enc_pos_max * c.enc_hidden, SELFTOK_ERR_BAD_ARG, "encoder.pos_embed shape");
+    int g = c.latent / c.enc_patch;
+    STK_TRY(dalloc(e, e->allocs, &e->enc_pos, (int64_t)g * g * c.enc_hidden));
+    STK_TRY(launch_crop_pos(pe->d, e->enc_pos, c.enc_pos_max, g, c.enc_hidden, s));
+    GETW(cb, "encoder.quantizer._codebook.embed");
+    STK_CHECK(cb->numel == (int64_t)c.codebook_size * c.code_dim, SELFTOK_ERR_BAD_ARG, "codebook shape");
+    STK_TRY(dalloc(e, e->allocs, &e->cbt, cb->numel));
+    STK_TRY(launch_transpose(cb->d, e->cbt, c.codebook_size, c.code_dim, s));
+  }
+  // ---- decoder tables
+  STK_TRY(dalloc(e, e->allocs, &e->ctx_mod, (int64_t)(L - 1 > 0 ? L - 1 : 1) * K * 6 * D));
+  for (int j = 0; j < L - 1; ++j)
+    STK_TRY(build_pos_table(e, "model.joint_blocks." + std::to_string(j) + ".context_block.", e->pos_freq, K, tmp1, tmp2,
+                            e->ctx_mod + (int64_t)j * K * 6 * D, s));
+  {
+    // csil = SiLU(t_embedder(t_freq)) [T, D]  (mmdit.py:1022; every consumer is Sequential(SiLU, Linear))
+    float* csil;
+    STK_TRY(dalloc(e, scratch, &csil, (int64_t)T * D));
+    Epilogue ep;
+    ep.act = ACT_SILU; ep.out = tmp1;
+    STK_TRY(lin32(e, "model.t_embedder.mlp.0", e->t_freq, 256, T, ep, s));
+    ep.out = csil;
+    STK_TRY(lin32(e, "model.t_embedder.mlp.2", tmp1, D, T, ep, s));
+    STK_TRY(dalloc(e, e->allocs, &e->x_mod, (int64_t)L * T * 6 * D));
+    for (int j = 0; j < L; ++j) {
+      Epilogue e2;
+      e2.out = e->x_mod + (int64_t)j * T * 6 * D;
+      STK_TRY(lin32(e, "model.joint_blocks." + std::to_string(j) + ".x_block.adaLN_modulation.1", csil, D, T, e2, s));
+    }
+    STK_TRY(dalloc(e, e->allocs, &e->ctx_last_mod, (int64_t)T * 2 * D));
+    Epilogue e3;
+    e3.out = e->ctx_last_mod;
+    STK_TRY(lin32(e, "model.joint_blocks." + std::to_string(L - 1) + ".context_block.adaLN_modulation.1", csil, D, T, e3, s));
+    STK_TRY(dalloc(e, e->allocs, &e->final_mod, (int64_t)T * 2 * D));
+    Epilogue e4;
+    e4.out = e->final_mod;
+    STK_TRY(lin32(e, "model.final_layer.adaLN_modulation.1", csil, D, T, e4, s));
+  }
+  if (c.renderer) {
+    GETW(pe, "model.positional_embedding");
+    GETW(mt, "model.mask_token");
+    STK_CHECK(pe->numel == (int64_t)e->Nimg * D && mt->numel == D, SELFTOK_ERR_UNSUPPORTED,
+              "renderer expects positional_embedding [N,D] and mask_token [1,1,D] (repeat=True)");
+    float* tmp;
+    STK_TRY(dalloc(e, scratch, &tmp, (int64_t)e->Nimg * D));
+    STK_TRY(dalloc(e, e->allocs, &e->rend_x0, (int64_t)e->Nimg * D));
+    STK_TRY(launch_bcast_rows(mt->d, nullptr, tmp, e->Nimg, 1, D, s));
+    STK_TRY(launch_bcast_rows(tmp, pe->d, e->rend_x0, 1, e->Nimg, D, s));
+  } else {
+    GETW(pe, "model.pos_embed");
+    STK_CHECK(pe->numel == (int64_t)c.dit_pos_max * c.dit_pos_max * D, SELFTOK_ERR_BAD_ARG, "model.pos_embed shape");
+    int g = c.latent / c.dit_patch;
+    STK_TRY(dalloc(e, e->allocs, &e->dit_pos, (int64_t)g * g * D));
+    STK_TRY(launch_crop_pos(pe->d, e->dit_pos, c.dit_pos_max, g, D, s));
+  }
+  // ---- tensor-core operand planes of the MMDiT linears
+  if (tc_mode(e)) {
+    const char* blocks[2] = {"context_block", "x_block"};
+    const char* lins[4] = {"attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2"};
+    for (int j = 0; j < L; ++j)
+      for (int b = 0; b < 2; ++b)
+        for (int l = 0; l < 4; ++l) {
+          if (j == L - 1 && b == 0 && l > 0) continue;          // pre_only context block: qkv only
+          std::string name = "model.joint_blocks." + std::to_string(j) + "." + blocks[b] + "." + lins[l] + ".weight";
+          GETW(W, name);
+          WPack p;
+          STK_TRY(dalloc(e, e->allocs, &p.hi, W->numel));
+          if (nsplit(e) == 3) STK_TRY(dalloc(e, e->allocs, &p.lo, W->numel));
+          STK_TRY(launch_split_bf16(W->d, p.hi, p.lo, W->numel, s));
+          e->wp[name] = p;
+        }
+  }
+  STK_CUDA(cudaStreamSynchronize(s));
+  for (void* p : scratch) cudaFree(p);
+  e->finalized = true;
+  return SELFTOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ encode
+static int ensure_ews(selftok_engine* e, int B) {
+  if (e->ews.B >= B) return 0;
+  free_ews(e);
+  EncodeWs& w = e->ews;
+  const selftok_config_t& c = e->cfg;
+  const int64_t Ni = e->Nenc, K = c.K, Hh = c.enc_hidden, Q = c.enc_qdim;
+  auto& P = w.allocs;
+  STK_TRY(dalloc(e, P, &w.x0, (int64_t)B * c.in_channels * c.latent * c.latent));
+  STK_TRY(dalloc(e, P, &w.patch, B * Ni * c.in_channels * c.enc_patch * c.enc_patch));
+  STK_TRY(dalloc(e, P, &w.x, B * Ni * Hh));
+  STK_TRY(dalloc(e, P, &w.q, B * K * Q));
+  STK_TRY(dalloc(e, P, &w.xn, B * Ni * Hh));
+  STK_TRY(dalloc(e, P, &w.qn, B * K * Q));
+  STK_TRY(dalloc(e, P, &w.xqkv, B * Ni * 3 * Hh));
+  STK_TRY(dalloc(e, P, &w.xkv, B * Ni * 2 * Q));
+  STK_TRY(dalloc(e, P, &w.qqkv, B * K * 3 * Q));
+  STK_TRY(dalloc(e, P, &w.xattn, B * Ni * Hh));
+  STK_TRY(dalloc(e, P, &w.qattn, B * K * Q));
+  STK_TRY(dalloc(e, P, &w.xh, B * Ni * 4 * Hh));
+  STK_TRY(dalloc(e, P, &w.qh, B * K * 4 * Q));
+  STK_TRY(dalloc(e, P, &w.outs_q, B * K * c.code_dim));
+  STK_TRY(dalloc(e, P, &w.tokens, B * K));
+  w.B = B;
+  return 0;
+}
+
+// Encoder.forward up to the quantizer input (models_ours.py:204-219,315-343; modules.py:310-327)
+static int encoder_features(selftok_engine* e, const float* x0, int B, cudaStream_t s) {
+  EncodeWs& w = e->ews;
+  const selftok_config_t& c = e->cfg;
+  const int Ni = e->Nenc, K = c.K, Hh = c.enc_hidden, Q = c.enc_qdim;
+  const int64_t Mx = (int64_t)B * Ni, Mq = (int64_t)B * K;
+  const float eps = 1e-6f;
+  STK_TRY(launch_patchify(x0, w.patch, B, c.in_channels, c.latent, c.latent, c.enc_patch, s));
+  {
+    Epilogue ep;
+    ep.out = w.x; ep.addtab = e->enc_pos; ep.add_ld = Hh; ep.add_period = Ni;
+    STK_TRY(lin32(e, "encoder.x_embedder.proj", w.patch, c.in_channels * c.enc_patch * c.enc_patch, Mx, ep, s));
+    GETW(qt, "encoder.query_tokens");
+    STK_CHECK(qt->numel == (int64_t)K * Q, SELFTOK_ERR_BAD_ARG, "query_tokens shape");
+    STK_TRY(launch_bcast_rows(qt->d, nullptr, w.q, B, K, Q, s));
+  }
+  for (int i = 0; i < c.enc_depth; ++i) {
+    const std::string p = "encoder.blocks." + std::to_string(i) + ".";
+    const float* mod = e->enc_mod + (int64_t)i * K * 6 * Q;     // [K][shift_msa|scale_msa|gate_msa|shift_mlp|scale_mlp|gate_mlp]
+    STK_TRY(launch_ln_mod(w.x, Hh, nullptr, nullptr, 0, 1, w.xn, nullptr, nullptr, Hh, Mx, Hh, eps, s));
+    STK_TRY(launch_ln_mod(w.q, Q, mod, mod + Q, 6 * Q, K, w.qn, nullptr, nullptr, Q, Mq, Q, eps, s));
+    Epilogue ep;
+    ep.out = w.xqkv; STK_TRY(lin32(e, p + "attn.qkv", w.xn, Hh, Mx, ep, s));
+    ep.out = w.xkv; STK_TRY(lin32(e, p + "attn.to_query_kv", w.xn, Hh, Mx, ep, s));
+    ep.out = w.qqkv; STK_TRY(lin32(e, p + "attn.query_linear", w.qn, Q, Mq, ep, s));
+    AttnOut ox;
+    ox.f32_a = w.xattn; ox.split = Ni; ox.ld = Hh;
+    STK_TRY(launch_attention_f32(w.xqkv, 3 * Hh, (int64_t)Ni * 3 * Hh, w.xqkv + Hh, w.xqkv + 2 * Hh, 3 * Hh, (int64_t)Ni * 3 * Hh, Ni,
+                                 nullptr, nullptr, 0, 0, 0, ox, B, Ni, c.enc_heads, Hh / c.enc_heads, 0, 0, s));
+    AttnOut oq;
+    oq.f32_a = w.qattn; oq.split = K; oq.ld = Q;
+    STK_TRY(launch_attention_f32(w.qqkv, 3 * Q, (int64_t)K * 3 * Q, w.xkv, w.xkv + Q, 2 * Q, (int64_t)Ni * 2 * Q, Ni,
+                                 w.qqkv + Q, w.qqkv + 2 * Q, 3 * Q, (int64_t)K * 3 * Q, K, oq, B, K, c.enc_qheads,
+                                 Q / c.enc_qheads, 0, 0, s));
+    // image stream: x += proj(x_attn); x += mlp(norm2(x))
+    Epilogue er;
+    er.mode = EPI_RESID; er.out = w.x; er.resid = w.x; er.ldo = Hh;
+    STK_TRY(lin32(e, p + "attn.proj", w.xattn, Hh, Mx, er, s));
+    STK_TRY(launch_ln_mod(w.x, Hh, nullptr, nullptr, 0, 1, w.xn, nullptr, nullptr, Hh, Mx, Hh, eps, s));
+    Epilogue eg;
+    eg.act = ACT_GELU; eg.out = w.xh;
+    STK_TRY(lin32(e, p + "mlp.fc1", w.xn, Hh, Mx, eg, s));
+    STK_TRY(lin32(e, p + "mlp.fc2", w.xh, 4 * Hh, Mx, er, s));
+    // query stream: q += gate_msa * query_proj(q_attn); q += gate_mlp * q_mlp(modulate(norm2(q)))
+    Epilogue eq;
+    eq.mode = EPI_RESID; eq.out = w.q; eq.resid = w.q; eq.ldo = Q; eq.gate = mod + 2 * Q; eq.gate_ld = 6 * Q; eq.gate_period = K;
+    STK_TRY(lin32(e, p + "attn.query_proj", w.qattn, Q, Mq, eq, s));
+    STK_TRY(launch_ln_mod(w.q, Q, mod + 3 * Q, mod + 4 * Q, 6 * Q, K, w.qn, nullptr, nullptr, Q, Mq, Q, eps, s));
+    eg.out = w.qh;
+    STK_TRY(lin32(e, p + "q_mlp.fc1", w.qn, Q, Mq, eg, s));
+    eq.gate = mod + 5 * Q;
+    STK_TRY(lin32(e, p + "q_mlp.fc2", w.qh, 4 * Q, Mq, eq, s));
+  }
+  return 0;
+}
+
+static int run_vq(selftok_engine* e, const float* z, int64_t R, int64_t* ids, float* outs_q, cudaStream_t s) {
+  const selftok_config_t& c = e->cfg;
+  GETW(wi, "encoder.quantizer.project_in.weight");
+  GETW(bi, "encoder.quantizer.project_in.bias");
+  GETW(cb, "encoder.quantizer._codebook.embed");
+  GETW(lw, "encoder.final_layer_norm3.weight");
+  GETW(lb, "encoder.final_layer_norm3.bias");
+  return launch_vq(z, R, c.enc_qdim, wi->d, bi->d, cb->d, e->cbt, c.codebook_size, c.code_dim, lw->d, lb->d, ids, outs_q, s);
+}
+
+#define HOT_PROLOGUE(e)                                                                  \
+  STK_CHECK(e, SELFTOK_ERR_BAD_ARG, "null handle");                                      \
+  STK_CHECK(e->finalized, SELFTOK_ERR_STATE, "selftok_finalize has not been called");    \
+  STK_CUDA(cudaSetDevice(e->cfg.device));                                                \
+  cudaStream_t s = (cudaStream_t)stream;                                                 \
+  const int64_t launches0 = g_launch_count;
+
+extern "C" __attribute__((visibility("default"))) int selftok_encode(selftok_handle_t e, const float* x0_dev, int B, int64_t* tokens_dev, float* outs_q_dev,
+                              float* feats_dev, void* stream) {
+  HOT_PROLOGUE(e);
+  STK_CHECK(x0_dev && tokens_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_encode: bad argument");
+  STK_TRY(ensure_ews(e, B));
+  STK_TRY(encoder_features(e, x0_dev, B, s));
+  const int64_t R = (int64_t)B * e->cfg.K;
+  STK_TRY(run_vq(e, e->ews.q, R, tokens_dev, outs_q_dev ? outs_q_dev : e->ews.outs_q, s));
+  if (feats_dev) STK_CUDA(cudaMemcpyAsync(feats_dev, e->ews.q, sizeof(float) * R * e->cfg.enc_qdim, cudaMemcpyDeviceToDevice, s));
+  e->last_launches = g_launch_count - launches0;
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_vq_argmax(selftok_handle_t e, const float* z_dev, int64_t R, int64_t* ids_dev, float* outs_q_dev,
+                                 void* stream) {
+  HOT_PROLOGUE(e);
+  STK_CHECK(z_dev && ids_dev && R > 0, SELFTOK_ERR_BAD_ARG, "selftok_vq_argmax: bad argument");
+  STK_TRY(run_vq(e, z_dev, R, ids_dev, outs_q_dev, s));
+  e->last_launches = g_launch_count - launches0;
+  return SELFTOK_OK;
+}
+
+static int run_lookup(selftok_engine* e, const int64_t* tokens, int B, float* outs_q, cudaStream_t s) {
+  GETW(cb, "encoder.quantizer._codebook.embed");
+  GETW(lw, "encoder.final_layer_norm3.weight");
+  GETW(lb, "encoder.final_layer_norm3.bias");
+  return launch_lookup_ln3(tokens, (int64_t)B * e->cfg.K, cb->d, e->cfg.codebook_size, e->cfg.code_dim, lw->d, lb->d, outs_q, s);
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_lookup(selftok_handle_t e, const int64_t* tokens_dev, int B, float* outs_q_dev, void* stream) {
+  HOT_PROLOGUE(e);
+  STK_CHECK(tokens_dev && outs_q_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_lookup: bad argument");
+  STK_TRY(run_lookup(e, tokens_dev, B, outs_q_dev, s));
+  e->last_launches = g_launch_count - launches0;
+  return SELFTOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+static int ensure_dws(selftok_engine* e, int B) {
+  if (e->dws.B >= B) return 0;
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);   // graphs hold pointers into the old workspace
+  e->graphs.clear();
+  free_dws(e);
+  DecodeWs& w = e->dws;
+  const selftok_config_t& c = e->cfg;
+  const int64_t K = c.K, N = e->Nimg, D = e->D, S = K + N;
+  auto& P = w.allocs;
+  STK_TRY(dalloc(e, P, &w.tokens, B * K));
+  STK_TRY(dalloc(e, P, &w.outs_q, B * K * c.code_dim));
+  STK_TRY(dalloc(e, P, &w.x_lat, (int64_t)B * c.in_channels * c.latent * c.latent));
+  STK_TRY(dalloc(e, P, &w.patch, B * N * c.in_channels * c.dit_patch * c.dit_patch));
+  STK_TRY(dalloc(e, P, &w.ctx0, B * K * D));
+  STK_TRY(dalloc(e, P, &w.ctx, B * K * D));
+  STK_TRY(dalloc(e, P, &w.x, B * N * D));
+  STK_TRY(dalloc(e, P, &w.qkv, B * S * 3 * D));
+  STK_TRY(dalloc(e, P, &w.o_final, B * N * c.dit_patch * c.dit_patch * c.in_channels));
+  STK_TRY(dalloc(e, P, &w.a_x, B * N * D));                       // fp32 LN output of the final layer (both modes)
+  if (!tc_mode(e)) {
+    STK_TRY(dalloc(e, P, &w.a_c, B * K * D));
+    STK_TRY(dalloc(e, P, &w.attn_c, B * K * D));
+    STK_TRY(dalloc(e, P, &w.attn_x, B * N * D));
+    STK_TRY(dalloc(e, P, &w.h_c, B * K * 4 * D));
+    STK_TRY(dalloc(e, P, &w.h_x, B * N * 4 * D));
+  } else {
+    const bool lo = nsplit(e) == 3;
+    STK_TRY(dalloc(e, P, &w.a_c_hi, B * K * D));
+    STK_TRY(dalloc(e, P, &w.a_x_hi, B * N * D));
+    STK_TRY(dalloc(e, P, &w.attn_c_hi, B * K * D));
+    STK_TRY(dalloc(e, P, &w.attn_x_hi, B * N * D));
+    STK_TRY(dalloc(e, P, &w.h_c_hi, B * K * 4 * D));
+    STK_TRY(dalloc(e, P, &w.h_x_hi, B * N * 4 * D));
+    if (lo) {
+      STK_TRY(dalloc(e, P, &w.a_c_lo, B * K * D));
+      STK_TRY(dalloc(e, P, &w.a_x_lo, B * N * D));
+      STK_TRY(dalloc(e, P, &w.attn_c_lo, B * K * D));
+      STK_TRY(dalloc(e, P, &w.attn_x_lo, B * N * D));
+      STK_TRY(dalloc(e, P, &w.h_c_lo, B * K * 4 * D));
+      STK_TRY(dalloc(e, P, &w.h_x_lo, B * N * 4 * D));
+    }
+  }
+  w.B = B;
+  return 0;
+}
+
+// One stream of one JointBlock: LN+modulate -> qkv GEMM into the joint buffer   (mmdit.py:441-483, 521-529)
+static int pre_attention(selftok_engine* e, const std::string& blk, const float* resid, int64_t M, const float* shift,
+                         const float* scale, int64_t ld_mod, int period, float* a32, bf16* a_hi, bf16* a_lo, int rpb_in,
+                         int S, int row_off, cudaStream_t s) {
+  const int D = e->D;
+  DecodeWs& w = e->dws;
+  Epilogue ep;
+  ep.out = w.qkv; ep.ldo = 3 * D; ep.rpb_in = rpb_in; ep.rpb_out = S; ep.row_off = row_off;
+  if (!tc_mode(e)) {
+    STK_TRY(launch_ln_mod(resid, D, shift, scale, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
+    return lin32(e, blk + "attn.qkv", a32, D, M, ep, s);
+  }
+  STK_TRY(launch_ln_mod(resid, D, shift, scale, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
+  return lintc(e, blk + "attn.qkv", a_hi, a_lo, M, ep, s);
+}
+
+// post_attention (mmdit.py:485-496): x += gate_msa*proj(attn); x += gate_mlp*mlp(modulate(norm2(x)))
+static int post_attention(selftok_engine* e, const std::string& blk, float* resid, int64_t M, const float* mod, int64_t ld_mod,
+                          int period, const float* attn32, const bf16* attn_hi, const bf16* attn_lo, float* a32, bf16* a_hi,
+                          bf16* a_lo, float* h32, bf16* h_hi, bf16* h_lo, cudaStream_t s) {
+  const int D = e->D;
+  Epilogue er;
+  er.mode = EPI_RESID; er.out = resid; er.resid = resid; er.ldo = D;
+  er.gate = mod + 2 * D; er.gate_ld = ld_mod; er.gate_period = period;
+  Epilogue eh;
+  eh.act = ACT_GELU;
+  if (!tc_mode(e)) {
+    STK_TRY(lin32(e, blk + "attn.proj", attn32, D, M, er, s));
+    STK_TRY(launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
+    eh.out = h32; eh.ldo = 4 * D;
+    STK_TRY(lin32(e, blk + "mlp.fc1", a32, D, M, eh, s));
+    er.gate = mod + 5 * D;
+    return lin32(e, blk + "mlp.fc2", h32, 4 * D, M, er, s);
+  }
+  STK_TRY(lintc(e, blk + "attn.proj", attn_hi, attn_lo, M, er, s));
+  STK_TRY(launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
+  eh.mode = EPI_SPLIT; eh.out_hi = h_hi; eh.out_lo = h_lo; eh.ldo = 4 * D;
+  STK_TRY(lintc(e, blk + "mlp.fc1", a_hi, a_lo, M, eh, s));
+  er.gate = mod + 5 * D;
+  return lintc(e, blk + "mlp.fc2", h_hi, h_lo, M, er, s);
+}
+
+// forward_core_with_concat (mmdit.py:918-933) on the residual streams already initialised in ws.ctx / ws.x.
+//   Kc         visible context rows (prefix; rows >= Kc are dropped — exact, SURVEY 8a note)
+//   step       row of the per-step tables (x adaLN, final adaLN, last-layer context adaLN)
+//   ctx_self   context rows attend to context keys only (renderer; mmdit.py:1581)
+static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_self, cudaStream_t s) {
+  const selftok_config_t& c = e->cfg;
+  DecodeWs& w = e->dws;
+  const int D = e->D, N = e->Nimg, L = c.dit_depth, T = e->steps, S = Kc + N;
+  const int64_t Mc = (int64_t)B * Kc, Mx = (int64_t)B * N;
+  for (int j = 0; j < L; ++j) {
+    const bool last = j == L - 1;
+    const std::string pc = "model.joint_blocks." + std::to_string(j) + ".context_block.";
+    const std::string px = "model.joint_blocks." + std::to_string(j) + ".x_block.";
+    const float* cmod = e->ctx_mod + (int64_t)j * c.K * 6 * D;                  // [K][6D]
+    const float* xmod = e->x_mod + ((int64_t)j * T + step) * 6 * D;             // [6D]
+    if (!last) {
+      STK_TRY(pre_attention(e, pc, w.ctx, Mc, cmod, cmod + D, 6 * D, Kc, w.a_c, w.a_c_hi, w.a_c_lo, Kc, S, 0, s));
+    } else {
+      const float* lm = e->ctx_last_mod + (int64_t)step * 2 * D;                // pre_only: (shift, scale) from c
+      STK_TRY(pre_attention(e, pc, w.ctx, Mc, lm, lm + D, 2 * D, 1, w.a_c, w.a_c_hi, w.a_c_lo, Kc, S, 0, s));
+    }
+    STK_TRY(pre_attention(e, px, w.x, Mx, xmod, xmod + D, 6 * D, 1, w.a_x, w.a_x_hi, w.a_x_lo, N, S, Kc, s));
+    AttnOut ao;
+    ao.split = Kc; ao.ld = D;
+    const int ctx_rows = ctx_self ? Kc : 0, ctx_keys = ctx_self ? Kc : 0;
+    if (!tc_mode(e)) {
+      ao.f32_a = w.attn_c; ao.f32_b = w.attn_x;
+      STK_TRY(launch_attention_f32(w.qkv, 3 * D, (int64_t)S * 3 * D, w.qkv + D, w.qkv + 2 * D, 3 * D, (int64_t)S * 3 * D, S,
+                                   nullptr, nullptr, 0, 0, 0, ao, B, S, e->H, 64, ctx_rows, ctx_keys, s));
+    } else {
+      ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
+      STK_TRY(launch_attention_tc(w.qkv, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s));
+    }
+    if (!last)
+      STK_TRY(post_attention(e, pc, w.ctx, Mc, cmod, 6 * D, Kc, w.attn_c, w.attn_c_hi, w.attn_c_lo, w.a_c, w.a_c_hi, w.a_c_lo,
+                             w.h_c, w.h_c_hi, w.h_c_lo, s));
+    STK_TRY(post_attention(e, px, w.x, Mx, xmod, 6 * D, 1, w.attn_x, w.attn_x_hi, w.attn_x_lo, w.a_x, w.a_x_hi, w.a_x_lo,
+                           w.h_x, w.h_x_hi, w.h_x_lo, s));
+  }
+  // FinalLayer (mmdit.py:641-645): fp32 FFMA (N = p*p*C = 64 columns)
+  const float* fm = e->final_mod + (int64_t)step * 2 * D;
+  STK_TRY(launch_ln_mod(w.x, D, fm, fm + D, 2 * D, 1, w.a_x, nullptr, nullptr, D, Mx, D, 1e-6f, s));
+  Epilogue ep;
+  ep.out = w.o_final;
+  return lin32(e, "model.final_layer.linear", w.a_x, D, Mx, ep, s);
+}
+
+// context_embedder(outs_q) + context_pos_embed (mmdit.py:1026) — step invariant, computed once per call
+static int context_embed(selftok_engine* e, int B, cudaStream_t s) {
+  DecodeWs& w = e->dws;
+  GETW(cp, "model.context_pos_embed");
+  STK_CHECK(cp->numel == (int64_t)e->cfg.K * e->D, SELFTOK_ERR_BAD_ARG, "context_pos_embed shape");
+  Epilogue ep;
+  ep.out = w.ctx0; ep.addtab = cp->d; ep.add_ld = e->D; ep.add_period = e->cfg.K;
+  return lin32(e, "model.context_embedder", w.outs_q, e->cfg.code_dim, (int64_t)B * e->cfg.K, ep, s);
+}
+
+// One MMDiT.forward (mmdit.py:992-1101) at schedule row `step` on ws.x_lat; leaves the patch outputs in ws.o_final.
+static int dit_forward(selftok_engine* e, int B, int step, cudaStream_t s) {
+  const selftok_config_t& c = e->cfg;
+  DecodeWs& w = e->dws;
+  const int D = e->D, N = e->Nimg, Kc = e->k[step] + 1;
+  STK_TRY(launch_patchify(w.x_lat, w.patch, B, c.in_channels, c.latent, c.latent, c.dit_patch, s));
+  Epilogue ep;
+  ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
+  STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
+  STK_TRY(launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
+  return joint_blocks(e, B, Kc, step, /*ctx_self=*/false, s);
+}
+
+static int decode_body(selftok_engine* e, int B, int steps, cudaStream_t s) {
+  const selftok_config_t& c = e->cfg;
+  DecodeWs& w = e->dws;
+  STK_TRY(run_lookup(e, w.tokens, B, w.outs_q, s));
+  STK_TRY(context_embed(e, B, s));
+  for (int i = 0; i < steps; ++i) {
+    STK_TRY(dit_forward(e, B, i, s));
+    // euler_step (rectified_flow.py:301-303): x <- x - (t_i - t_{i+1}) * v, fused with unpatchify
+    STK_TRY(launch_unpatchify_axpy(w.o_final, w.x_lat, w.x_lat, e->dt[i], B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+  }
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_set_use_graph(selftok_handle_t e, int enable) {
+  STK_CHECK(e, SELFTOK_ERR_BAD_ARG, "null handle");
+  e->use_graph = enable != 0;
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_decode(selftok_handle_t e, const int64_t* tokens_dev, const float* noise_dev, int B, int steps,
+                              float* x0_out_dev, void* stream) {
+  HOT_PROLOGUE(e);
+  STK_CHECK(tokens_dev && noise_dev && x0_out_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_decode: bad argument");
+  STK_CHECK(!e->cfg.renderer, SELFTOK_ERR_STATE, "handle was created for the renderer; use selftok_render");
+  STK_CHECK(steps > 0 && steps <= e->steps, SELFTOK_ERR_BAD_ARG, "steps exceeds the schedule");
+  STK_TRY(ensure_dws(e, B));
+  DecodeWs& w = e->dws;
+  const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
+  if (tokens_dev != w.tokens) STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_dev, sizeof(int64_t) * B * e->cfg.K, cudaMemcpyDeviceToDevice, s));
+  if (noise_dev != w.x_lat) STK_CUDA(cudaMemcpyAsync(w.x_lat, noise_dev, sizeof(float) * nlat, cudaMemcpyDeviceToDevice, s));
+  if (!e->use_graph) {
+    STK_TRY(decode_body(e, B, steps, s));
+    e->last_launches = g_launch_count - launches0;
+  } else {
+    auto key = std::make_pair(B, steps);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      cudaStream_t cs;
+      STK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      STK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const int64_t l0 = g_launch_count;
+      int st = decode_body(e, B, steps, cs);
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (st != 0) { if (graph) cudaGraphDestroy(graph); return st; }
+      STK_CUDA(ce);
+      cudaGraphExec_t exec;
+      STK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = e->graphs.emplace(key, std::make_pair(exec, g_launch_count - l0)).first;
+    }
+    STK_CUDA(cudaGraphLaunch(it->second.first, s));
+    e->last_launches = it->second.second;
+  }
+  if (x0_out_dev != w.x_lat) STK_CUDA(cudaMemcpyAsync(x0_out_dev, w.x_lat, sizeof(float) * nlat, cudaMemcpyDeviceToDevice, s));
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_dit_velocity(selftok_handle_t e, const int64_t* tokens_dev, const float* x_dev, int B, int step,
+                                    float* v_out_dev, void* stream) {
+  HOT_PROLOGUE(e);
+  STK_CHECK(tokens_dev && x_dev && v_out_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_dit_velocity: bad argument");
+  STK_CHECK(!e->cfg.renderer, SELFTOK_ERR_STATE, "renderer handle");
+  STK_CHECK(step >= 0 && step < e->steps, SELFTOK_ERR_BAD_ARG, "step out of range");
+  STK_TRY(ensure_dws(e, B));
+  DecodeWs& w = e->dws;
+  const selftok_config_t& c = e->cfg;
+  const int64_t nlat = (int64_t)B * c.in_channels * c.latent * c.latent;
+  STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_dev, sizeof(int64_t) * B * c.K, cudaMemcpyDeviceToDevice, s));
+  STK_CUDA(cudaMemcpyAsync(w.x_lat, x_dev, sizeof(float) * nlat, cudaMemcpyDeviceToDevice, s));
+  STK_TRY(run_lookup(e, w.tokens, B, w.outs_q, s));
+  STK_TRY(context_embed(e, B, s));
+  STK_TRY(dit_forward(e, B, step, s));
+  STK_TRY(launch_unpatchify_axpy(w.o_final, nullptr, v_out_dev, -1.f, B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+  e->last_launches = g_launch_count - launches0;
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_render(selftok_handle_t e, const int64_t* tokens_dev, int B, float* x0_out_dev, void* stream) {
+  HOT_PROLOGUE(e);
+  STK_CHECK(tokens_dev && x0_out_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_render: bad argument");
+  STK_CHECK(e->cfg.renderer, SELFTOK_ERR_STATE, "handle was not created for the renderer");
+  STK_TRY(ensure_dws(e, B));
+  DecodeWs& w = e->dws;
+  const selftok_config_t& c = e->cfg;
+  if (tokens_dev != w.tokens) STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_dev, sizeof(int64_t) * B * c.K, cudaMemcpyDeviceToDevice, s));
+  STK_TRY(run_lookup(e, w.tokens, B, w.outs_q, s));
+  STK_TRY(context_embed(e, B, s));
+  // x = mask_token + positional_embedding (mmdit.py:1518-1522); context = full K rows, context rows see context only
+  STK_TRY(launch_bcast_rows(e->rend_x0, nullptr, w.x, B, e->Nimg, e->D, s));
+  STK_TRY(launch_copy_rows(w.ctx0, (int64_t)c.K * e->D, w.ctx, (int64_t)c.K * e->D, B, (int64_t)c.K * e->D, s));
+  STK_TRY(joint_blocks(e, B, c.K, 0, /*ctx_self=*/true, s));
+  STK_TRY(launch_unpatchify_axpy(w.o_final, nullptr, x0_out_dev, -1.f, B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+  e->last_launches = g_launch_count - launches0;
+  return SELFTOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ host-buffer variants
+extern "C" __attribute__((visibility("default"))) int selftok_encode_host(selftok_handle_t e, const float* x0_host, int B, int64_t* tokens_host, void* stream) {
+  STK_CHECK(e && x0_host && tokens_host && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_encode_host: bad argument");
+  STK_CHECK(e->finalized, SELFTOK_ERR_STATE, "selftok_finalize has not been called");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  STK_TRY(ensure_ews(e, B));
+  const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
+  STK_CUDA(cudaMemcpyAsync(e->ews.x0, x0_host, sizeof(float) * nlat, cudaMemcpyHostToDevice, s));
+  STK_TRY(selftok_encode(e, e->ews.x0, B, e->ews.tokens, nullptr, nullptr, stream));
+  STK_CUDA(cudaMemcpyAsync(tokens_host, e->ews.tokens, sizeof(int64_t) * B * e->cfg.K, cudaMemcpyDeviceToHost, s));
+  STK_CUDA(cudaStreamSynchronize(s));
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_decode_host(selftok_handle_t e, const int64_t* tokens_host, const float* noise_host, int B, int steps,
+                                   float* x0_out_host, void* stream) {
+  STK_CHECK(e && tokens_host && noise_host && x0_out_host && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_decode_host: bad argument");
+  STK_CHECK(e->finalized, SELFTOK_ERR_STATE, "selftok_finalize has not been called");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  STK_TRY(ensure_dws(e, B));
+  DecodeWs& w = e->dws;
+  const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
+  STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_host, sizeof(int64_t) * B * e->cfg.K, cudaMemcpyHostToDevice, s));
+  STK_CUDA(cudaMemcpyAsync(w.x_lat, noise_host, sizeof(float) * nlat, cudaMemcpyHostToDevice, s));
+  STK_TRY(selftok_decode(e, w.tokens, w.x_lat, B, steps, w.x_lat, stream));
+  STK_CUDA(cudaMemcpyAsync(x0_out_host, w.x_lat, sizeof(float) * nlat, cudaMemcpyDeviceToHost, s));
+  STK_CUDA(cudaStreamSynchronize(s));
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_render_host(selftok_handle_t e, const int64_t* tokens_host, int B, float* x0_out_host, void* stream) {
+  STK_CHECK(e && tokens_host && x0_out_host && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_render_host: bad argument");
+  STK_CHECK(e->finalized, SELFTOK_ERR_STATE, "selftok_finalize has not been called");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  STK_TRY(ensure_dws(e, B));
+  DecodeWs& w = e->dws;
+  const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
+  STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_host, sizeof(int64_t) * B * e->cfg.K, cudaMemcpyHostToDevice, s));
+  STK_TRY(selftok_render(e, w.tokens, B, w.x_lat, stream));
+  STK_CUDA(cudaMemcpyAsync(x0_out_host, w.x_lat, sizeof(float) * nlat, cudaMemcpyDeviceToHost, s));
+  STK_CUDA(cudaStreamSynchronize(s));
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t selftok_last_launch_count(selftok_handle_t e) { return e ? e->last_launches : -1; }
+extern "C" __attribute__((visibility("default"))) int64_t selftok_device_bytes(selftok_handle_t e) { return e ? e->bytes : -1; }
+
+// ------------------------------------------------------------------------------------------------ kernel-level ABI
+extern "C" __attribute__((visibility("default"))) int selftok_k_linear_f32(const float* A, const float* W, const float* bias, float* out, int64_t M, int N, int K,
+                                    int act, void* stream) {
+  Epilogue ep;
+  ep.act = act; ep.bias = bias; ep.out = out; ep.ldo = N;
+  return launch_linear_f32(A, K, W, K, M, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_k_linear_tc(const float* A, const float* W, const float* bias, float* out, int64_t M, int N, int K,
+                                   int ns, void* stream) {
+  STK_CHECK(A && W && out && (ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_linear_tc: bad argument");
+  STK_TRY(gemm_tc_init());
+  cudaStream_t s = (cudaStream_t)stream;
+  bf16 *ah, *al = nullptr, *wh, *wl = nullptr;
+  STK_CUDA(cudaMalloc(&ah, sizeof(bf16) * M * K));
+  STK_CUDA(cudaMalloc(&wh, sizeof(bf16) * (int64_t)N * K));
+  if (ns == 3) {
+    STK_CUDA(cudaMalloc(&al, sizeof(bf16) * M * K));
+    STK_CUDA(cudaMalloc(&wl, sizeof(bf16) * (int64_t)N * K));
+  }
+  int st = launch_split_bf16(A, ah, al, M * K, s);
+  if (!st) st = launch_split_bf16(W, wh, wl, (int64_t)N * K, s);
+  Epilogue ep;
+  ep.bias = bias; ep.out = out; ep.ldo = N;
+  if (!st) st = launch_gemm_tc(ah, al, wh, wl, M, N, K, ns, ep, s);
+  cudaStreamSynchronize(s);
+  cudaFree(ah); cudaFree(wh);
+  if (al) cudaFree(al);
+  if (wl) cudaFree(wl);
+  return st;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_k_ln_mod_f32(const float* x, const float* shift, const float* scale, int64_t ld_mod, int period,
+                                    float* out, int64_t M, int D, void* stream) {
+  return launch_ln_mod(x, D, shift, scale, ld_mod, period, out, nullptr, nullptr, D, M, D, 1e-6f, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_k_attention_f32(const float* q, int64_t q_ld, const float* k1, const float* v1, int64_t kv1_ld, int S1,
+                                       const float* k2, const float* v2, int64_t kv2_ld, int S2, float* out, int64_t out_ld,
+                                       int B, int Sq, int H, int hd, void* stream) {
+  AttnOut ao;
+  ao.f32_a = out; ao.split = Sq; ao.ld = out_ld;
+  return launch_attention_f32(q, q_ld, (int64_t)Sq * q_ld, k1, v1, kv1_ld, (int64_t)S1 * kv1_ld, S1, k2, v2, kv2_ld,
+                              (int64_t)S2 * kv2_ld, S2, ao, B, Sq, H, hd, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(const float* qkv, float* out, int B, int S, int H, int ns, int ctx_rows, int ctx_keys,
+                                      void* stream) {
+  STK_CHECK(qkv && out && (ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
+  AttnOut ao;
+  ao.f32_a = out; ao.split = S; ao.ld = (int64_t)H * 64;
+  return launch_attention_tc(qkv, B, S, H, ns, ctx_rows, ctx_keys, ao, (cudaStream_t)stream);
+}

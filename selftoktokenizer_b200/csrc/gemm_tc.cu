@@ -1,0 +1,395 @@
+// tcgen05 GEMM of the MMDiT linears (sm_100a):  y = A W^T (+bias, fused epilogue), fp32 accumulation in TMEM.
+//
+//   operands   bf16 planes, K-major.  NSPLIT == 1: y = A_hi W_hi^T.  NSPLIT == 3 ("bf16x3", fp32-faithful to ~2^-17):
+//              y = A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T, all three products accumulated into the same TMEM tile.
+//   tile       128 x 256 x 64 per pipeline stage, UMMA 128x256x16 (kind::f16, cta_group::1)
+//   staging    TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) -> shared memory ring, mbarrier full/empty pairs
+//   roles      warp 0: TMA producer (1 thread) | warp 1: MMA issuer (1 thread) | warps 2-5: epilogue (TMEM -> regs -> HBM)
+//   TMEM       512 columns = 2 accumulator tiles; the epilogue of tile i overlaps the MMAs of tile i+1
+//   schedule   persistent CTAs (grid = #SMs), tiles rasterised in groups of 8 M-blocks for L2 reuse of W
+//
+// Replaces the cuBLAS SGEMMs behind nn.Linear in DismantledBlock (sd3/mmdit.py:266,269,293,301; other_impls.py:82-84)
+// together with the elementwise kernels around them (bias, GELU-tanh, gate*y + residual; mmdit.py:485-496).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cuda.h>   // CUtensorMap types only; the driver entry point is resolved at run time (no -lcuda)
+
+namespace stk {
+
+namespace {
+
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;      // 16 KiB
+constexpr int B_TILE_BYTES = BN * BK * 2;      // 32 KiB
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+
+template <int NSPLIT> struct Cfg {
+  static constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);     // 48 KiB / 96 KiB
+  static constexpr int STAGES = NSPLIT == 3 ? 2 : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 8000000000LL) {
+      printf("selftok gemm_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory operand descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (8 rows * 128 B = 1024)
+//   [46,48) version = 1 (sm_100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1),
+// both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmParams {
+  int64_t M;
+  int N, K;
+  Epilogue ep;
+};
+
+__device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
+  constexpr int GM = 8;
+  const int per_group = GM * n_tiles;
+  const int group = t / per_group;
+  const int first_m = group * GM;
+  const int gm = min(GM, m_tiles - first_m);
+  const int local = t - group * per_group;
+  m_blk = first_m + local % gm;
+  n_blk = local / gm;
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+template <int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+               const GemmParams p) {
+  using C = Cfg<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;           // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (int)((p.M + BM - 1) / BM), n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int nk = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (NSPLIT == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t fb = full_bar(stage);
+          mbar_expect_tx(fb, C::STAGE_BYTES);
+          tma_load_2d(sa, &map_a_hi, fb, kb * BK, m_blk * BM);
+          tma_load_2d(sa + C::PLANES * A_TILE_BYTES, &map_b_hi, fb, kb * BK, n_blk * BN);
+          if (NSPLIT == 3) {
+            tma_load_2d(sa + A_TILE_BYTES, &map_a_lo, fb, kb * BK, m_blk * BM);
+            tma_load_2d(sa + 2 * A_TILE_BYTES + B_TILE_BYTES, &map_b_lo, fb, kb * BK, n_blk * BN);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);               // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb_hi = sa_hi + C::PLANES * A_TILE_BYTES;
+          const uint32_t sa_lo = sa_hi + A_TILE_BYTES;
+          const uint32_t sb_lo = sb_hi + B_TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;                // bytes inside the 128 B swizzle row
+            const uint64_t da_hi = make_smem_desc(sa_hi + koff), db_hi = make_smem_desc(sb_hi + koff);
+            tc_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (NSPLIT == 3) {
+              const uint64_t da_lo = make_smem_desc(sa_lo + koff), db_lo = make_smem_desc(sb_lo + koff);
+              tc_mma_f16(d_tmem, da_hi, db_lo, idesc, 1u);
+              tc_mma_f16(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          tc_commit(empty_bar(stage));                           // smem slot reusable once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));                               // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps 2..5 (TMEM lane quarter = warp % 4)
+    const int quarter = warp & 3;
+    const Epilogue& e = p.ep;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      int m_blk, n_blk;
+      tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)m_blk * BM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      int64_t orow = m;
+      if (e.rpb_in > 0) orow = (m / e.rpb_in) * e.rpb_out + e.row_off + (m % e.rpb_in);
+      const float* gate_row = (e.mode == EPI_RESID && e.gate) ? e.gate + (m % e.gate_period) * e.gate_ld : nullptr;
+      const float* add_row = (e.mode == EPI_STORE && e.addtab) ? e.addtab + (m % e.add_period) * e.add_ld : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;                                    // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const bool full = n0 + 32 <= p.N;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = n0 + j4 * 4 + j;
+              float v = __uint_as_float(r[j4 * 4 + j]);
+              if (full || n < p.N) {
+                if (e.bias) v += e.bias[n];
+                v = apply_act(v, e.act);
+              }
+              y[j] = v;
+            }
+            const int n = n0 + j4 * 4;
+            if (full || n + 3 < p.N) {
+              if (e.mode == EPI_STORE) {
+                if (add_row) { float4 a = *reinterpret_cast<const float4*>(add_row + n); y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; }
+                *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = make_float4(y[0], y[1], y[2], y[3]);
+              } else if (e.mode == EPI_RESID) {
+                float4 g = gate_row ? *reinterpret_cast<const float4*>(gate_row + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+                float4 x = *reinterpret_cast<const float4*>(e.resid + orow * e.ldo + n);
+                x.x += g.x * y[0]; x.y += g.y * y[1]; x.z += g.z * y[2]; x.w += g.w * y[3];
+                *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = x;
+              } else {
+                __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
+                *reinterpret_cast<uint2*>(e.out_hi + orow * e.ldo + n) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+                if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + orow * e.ldo + n) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+              }
+            } else {
+              for (int j = 0; j < 4; ++j) {
+                const int nn = n + j;
+                if (nn >= p.N) break;
+                if (e.mode == EPI_STORE) {
+                  e.out[orow * e.ldo + nn] = y[j] + (add_row ? add_row[nn] : 0.f);
+                } else if (e.mode == EPI_RESID) {
+                  e.out[orow * e.ldo + nn] = e.resid[orow * e.ldo + nn] + (gate_row ? gate_row[nn] : 1.f) * y[j];
+                } else {
+                  __nv_bfloat16 hh, ll;
+                  split_bf16(y[j], hh, ll);
+                  e.out_hi[orow * e.ldo + nn] = hh;
+                  if (e.out_lo) e.out_lo[orow * e.ldo + nn] = ll;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+
+int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, int box_rows) {
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -5;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  STK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  STK_CHECK(fn && qres == cudaDriverEntryPointSuccess, -5, "cuTensorMapEncodeTiled not available from the driver");
+  int dev = 0;
+  STK_CUDA(cudaGetDevice(&dev));
+  STK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  STK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
+  STK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* W_hi,
+                   const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
+                   cudaStream_t s) {
+  STK_CHECK(g_encode, -3, "gemm_tc_init has not been called");
+  STK_CHECK(A_hi && W_hi && M > 0 && N > 0 && K > 0, -1, "gemm_tc: bad arguments");
+  STK_CHECK(nsplit == 1 || (nsplit == 3 && A_lo && W_lo), -1, "gemm_tc: nsplit must be 1, or 3 with lo planes");
+  STK_CHECK(K % 8 == 0, -2, "gemm_tc: K must be a multiple of 8 (16-byte TMA row pitch)");
+  STK_CHECK(ep.ldo % 4 == 0 && N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");
+  STK_CHECK(ep.mode != EPI_RESID || ep.gate == nullptr || ep.gate_ld % 4 == 0, -2, "gemm_tc: gate pitch must be a multiple of 4");
+  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  STK_TRY(make_map(&ma_hi, A_hi, M, K, BM));
+  STK_TRY(make_map(&mb_hi, W_hi, N, K, BN));
+  if (nsplit == 3) {
+    STK_TRY(make_map(&ma_lo, A_lo, M, K, BM));
+    STK_TRY(make_map(&mb_lo, W_lo, N, K, BN));
+  } else {
+    ma_lo = ma_hi; mb_lo = mb_hi;
+  }
+  GemmParams p{M, N, K, ep};
+  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (nsplit == 3)
+    gemm_tc_kernel<3><<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  else
+    gemm_tc_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  count_launch();
+  STK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace stk

@@ -1,0 +1,184 @@
+"""Drop-in `SelftokPipeline` for the encode / decode path of mimogpt/infer/SelftokPipeline.py.
+
+Same constructor signature, attributes and method contracts as the reference class (SelftokPipeline.py:153-322):
+
+    encoding(images [B,3,H,W] in [-1,1], device)            -> tokens [B,K] int64 on device          (:210-225)
+    decoding(idx numpy [B,K] int64, device)                 -> images [B,3,H,W] in [0,1], self.dtype (:227-294)
+    decoding_with_renderer(idx, device)                     -> same, one renderer pass               (:296-322)
+
+Everything between the VAE calls runs in the CUDA library behind include/selftok_b200.h; the host keeps what the
+reference keeps on the host: YAML/config, checkpoint loading, the SD3 VAE (diffusers; outside the measured path,
+SURVEY 8f), the CPU-generator noise draw (:262-264) and numpy<->tensor conversion.  The latent-boundary methods
+`encode_latents` / `decode_latents` / `render_latents` are the same calls without the VAE and are what the parity
+tests and bench.py measure.
+
+Reference quirks consciously NOT reproduced (documented in DESIGN.md): cfg is not mutated; the sampler does not
+re-run encoder+VQ on the noise every step (rectified_flow.py:212-215, dead for the output); quantizer.steps/count
+buffers are not incremented; no host syncs inside the loop.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from .capi import Engine, SelftokError
+from .config import SelftokDims
+from . import schedule as sched
+
+
+class NormalizeToTensor(object):
+    """uint8 HWC image -> float CHW in [-1,1]; same arithmetic as SelftokPipeline.py:85-97."""
+
+    def __init__(self, reshape=True):
+        self.reshape = reshape
+
+    def __call__(self, image):
+        image = np.array(image).astype(np.float32)
+        image = (image / 127.5 - 1.0).astype(np.float32)
+        if self.reshape:
+            image = np.reshape(image, (image.shape[0], image.shape[1], -1))
+        image = image.transpose((2, 0, 1))
+        return torch.from_numpy(image)
+
+
+def norm_ip(img, low, high):
+    # SelftokPipeline.py:135-137
+    img.clamp_(min=low, max=high)
+    img.sub_(low).div_(max(high - low, 1e-5))
+
+
+class SD3LatentFormat:
+    """sd3/sd3_impls.py:133-144"""
+    scale_factor = 1.5305
+    shift_factor = 0.0609
+
+    def process_in(self, latent):
+        return (latent - self.shift_factor) * self.scale_factor
+
+    def process_out(self, latent):
+        return (latent / self.scale_factor) + self.shift_factor
+
+
+def _load_vae(sd3_path, device, dtype):
+    try:
+        from diffusers import AutoencoderKL  # noqa: WPS433 (optional, external weights)
+    except Exception as exc:  # pragma: no cover - diffusers is not in the build image
+        raise SelftokError("the pixel-space API needs diffusers.AutoencoderKL (SD3 VAE); use the *_latents methods "
+                           "at the latent boundary instead") from exc
+    vae = AutoencoderKL.from_pretrained(sd3_path, subfolder="vae")
+    vae.to(device).to(dtype)
+    vae.eval()
+    return vae
+
+
+def _decoder_state(state_dict: Dict, ema_decoder: bool) -> Dict[str, torch.Tensor]:
+    """Checkpoint layout (SelftokPipeline.py:190-195): 'encoder.*' / 'model.*' (+ optional 'ema_state_dict' holding the
+    MMDiT without the 'model.' prefix, loaded into a deep copy of self.model.model)."""
+    sd = {k: v for k, v in state_dict.items() if torch.is_tensor(v)}
+    if ema_decoder:
+        ema = state_dict["ema_state_dict"]
+        sd = {k: v for k, v in sd.items() if not k.startswith("model.")}
+        sd.update({"model." + k: v for k, v in ema.items()})
+    return sd
+
+
+class SelftokPipeline:
+    def __init__(self, cfg, ckpt_path, sd3_path, datasize=256, start=1.0, cfg_scale=1, model_type="sd3",
+                 dtype=torch.bfloat16, ema_decoder=False, device=None, *, state_dict=None, vae=None,
+                 precision="bf16x3", dims: Optional[SelftokDims] = None):
+        self.cfg = cfg
+        self.datasize = datasize
+        self.model_type = model_type
+        self.dtype = dtype
+        if self.model_type != "sd3":
+            raise ValueError(f"Unsupported MODEL_TYPE: {self.model_type}. Expected 'sd3'")
+        if cfg_scale != 1:
+            raise SelftokError("cfg_scale != 1 is not on the shipped path (the reference never forwards it: "
+                               "rectified_flow.py:173 default uncond_scale=1.0)")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.dims = dims if dims is not None else SelftokDims.from_cfg(cfg)
+        self.vae = vae
+        if self.vae is None and sd3_path:
+            self.vae = _load_vae(sd3_path, self.device, self.dtype)
+        self.ema_decoder = ema_decoder
+        self.K = self.dims.K
+        self.count = 0
+        self.count_cfg = 0
+        self.start = start
+        self.cfg_scale = cfg_scale
+        p = cfg["tokenizer"]["params"] if cfg is not None else {}
+        self.cut_of_k = p.get("cut_of_k", None) or None
+        if self.cut_of_k is not None:
+            raise SelftokError("cut_of_k is not on the shipped path")
+        if state_dict is None:
+            state_dict = torch.load(ckpt_path, map_location="cpu")
+        print("Loading all...")
+        self._steps = 50
+        self.engine = Engine(self.dims, _decoder_state(state_dict, ema_decoder), device=self.device,
+                             precision=precision, steps=self._steps, start=self.start)
+        self.diti = sched.DiTiCont(1000, self.dims.K, self.dims.stages, self.dims.k_per_stage)
+        self.flow = self.engine.tables           # scheduled t / dt / k tables (RectifiedFlow.make_schedule equivalent)
+        self.cond_vary = True
+        self.saved_images = 8
+
+    # ------------------------------------------------------------------ latent-boundary API (the measured path)
+    @torch.no_grad()
+    def encode_latents(self, x_0: torch.Tensor) -> torch.Tensor:
+        """x_0 = SD3LatentFormat().process_in(vae.encode(images).mode()).float() -> tokens [B,K] int64 (device)."""
+        return self.engine.encode(x_0)
+
+    @torch.no_grad()
+    def decode_latents(self, idx, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tokens -> pred_x0 latents after the 50-step Euler loop.  `noise` defaults to the reference's draw:
+        torch.randn on the CPU global generator, then moved to the device (SelftokPipeline.py:262-264)."""
+        token_idx = torch.from_numpy(idx) if isinstance(idx, np.ndarray) else idx
+        B = token_idx.shape[0]
+        latent_dim = self.datasize // 8
+        if noise is None:
+            noise = torch.randn(B, self.dims.in_channels, latent_dim, latent_dim)
+        return self.engine.decode(token_idx, noise)
+
+    @torch.no_grad()
+    def render_latents(self, idx) -> torch.Tensor:
+        token_idx = torch.from_numpy(idx) if isinstance(idx, np.ndarray) else idx
+        return self.engine.render(token_idx)
+
+    # ------------------------------------------------------------------ reference API (pixel space, needs the SD3 VAE)
+    def _need_vae(self):
+        if self.vae is None:
+            raise SelftokError("no VAE: pass sd3_path (diffusers AutoencoderKL) or vae=..., or use the *_latents methods")
+
+    def encoding(self, images, device):
+        print("Begin encoding.")
+        self._need_vae()
+        images = images.to(dtype=self.dtype, device=device)
+        x_0 = self.vae.encode(images, return_dict=False)[0].mode()
+        x_0 = SD3LatentFormat().process_in(x_0)
+        x_0 = x_0.to(torch.float32)
+        tokens = self.encode_latents(x_0)
+        print("End encoding.")
+        return tokens
+
+    @torch.no_grad()
+    def decoding(self, idx, device):
+        print("Begin decoding.")
+        self._need_vae()
+        pred_x0 = self.decode_latents(idx)
+        pred_x0_out = SD3LatentFormat().process_out(pred_x0).to(self.dtype)
+        recons = self.vae.decode(pred_x0_out, return_dict=False)[0]
+        norm_ip(recons, -1, 1)
+        print("End decoding.")
+        return recons
+
+    @torch.no_grad()
+    def decoding_with_renderer(self, idx, device):
+        print("Begin decoding with Renderer.")
+        self._need_vae()
+        pred_x0 = self.render_latents(idx)
+        pred_x0_out = SD3LatentFormat().process_out(pred_x0).to(self.dtype)
+        recons = self.vae.decode(pred_x0_out)[0]
+        norm_ip(recons, -1, 1)
+        print("End decoding with Renderer.")
+        return recons
