@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Selftok hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU arithmetic on the host cores
+
+One "step" = one pass of the hot path over one batch: encode (16-block Q-Former + fused VQ -> 512 tokens) followed by
+the 50-step rectified-flow decode of those tokens (24-layer MMDiT), 256x256 images, no VAE (latent boundary).
+Workload at N = 1: BASELINE.json configs[2], batch 64.  N > 1: the same batch per GPU (weak scaling), weights
+replicated, one NCCL all-gather of the token ids per step.  Synthetic latents and a seeded synthetic
+checkpoint of the real architecture (no weights are obtainable offline).
+
+Printed JSON (rank 0, one line): metric/value/unit/... per the driver contract, plus
+  e2e          the same metric through the host-buffer C-ABI entry points (pinned host -> device copies of latents,
+               tokens and noise and the device -> host reads of tokens and latents inside the timed region)
+  roofline     tcgen05 GEMM class (dominant kernel): algorithmic FLOPs / summed CUDA-event time of its launches in one
+               profiled step, against MEASURED_PEAKS.json's sustained bf16 GEMM rate
+  cpu_baseline oracle port of the reference arithmetic (torch fp32 on the host cores) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+from selftoktokenizer_b200 import config as C  # noqa: E402
+from selftoktokenizer_b200 import schedule as S  # noqa: E402
+from selftoktokenizer_b200 import synth  # noqa: E402
+
+METRIC = "images/sec encode+50-step decode, 256x256/512-tok"
+UNIT = "images/s"
+BATCH = 64
+DECODE_STEPS = 50
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), tflops_burst=float(d["bf16_tflops"]),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json, sustained bf16 cuBLAS)")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def gemm_flops_per_step(B: int) -> float:
+    """Algorithmic (single-product, masked-effective) FLOPs of the tcgen05 GEMM launches of one 50-step decode:
+    per layer and stream qkv 2*M*D*3D, proj 2*M*D*D, fc1+fc2 16*M*D*D; the last layer's context stream is qkv only."""
+    d = C.FULL
+    tb = S.make_tables(d.K, d.stages, d.k_per_stage, DECODE_STEPS)
+    D, N, L = d.dit_hidden, d.n_img, d.dit_depth
+    f = 0.0
+    for i in range(DECODE_STEPS):
+        kc = int(tb.k[i]) + 1
+        for j in range(L):
+            f += B * N * (6 * D * D + 2 * D * D + 16 * D * D)
+            f += B * kc * (6 * D * D + (0 if j == L - 1 else 2 * D * D + 16 * D * D))
+    return f
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample(n_threads=None):
+    """Bounded sample of the reference arithmetic on the host: B=1 full-geometry encode + the first decode step
+    (k = 511, all tokens visible), including the reference's per-step dead encoder+VQ call (rectified_flow.py:212-215).
+    Extrapolated to 50 steps with the per-step FLOP model; returns images/s and the sample description."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    import selftok_oracle as O
+    if n_threads:
+        torch.set_num_threads(n_threads)
+    d = C.FULL
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sd = {k: v.cpu() for k, v in synth.synth_state_dict(d, device=dev).items()}
+    tb = S.make_tables(d.K, d.stages, d.k_per_stage, DECODE_STEPS)
+    x0 = synth.synth_tensor("bench.cpu.x0", (1, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    noise = synth.synth_tensor("bench.cpu.noise", (1, d.in_channels, d.latent, d.latent), "emb", 1.0)
+
+    def one():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            outs_q, tok, _ = O.encode(sd, d, x0, tb)
+            t1 = time.perf_counter()
+            O.decode(sd, d, tok, noise, steps=DECODE_STEPS, tables=tb, n_steps_run=1, replay_dead_encoder_call=True)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    eff = []
+    D, N, L = d.dit_hidden, d.n_img, d.dit_depth
+    for i in range(DECODE_STEPS):       # the reference computes the DENSE K+N sequence every step (masked, not dropped)
+        eff.append(sum(S.dense_flops_per_image_step(D, d.K, N, j == L - 1) for j in range(L)))
+    scale = sum(eff) / eff[0]
+    return one, scale
+
+
+def run_reference(args):
+    """--impl reference: the reference's own arithmetic (oracle port, torch fp32 CPU) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    one, scale = cpu_sample(cores)
+    for _ in range(args.warmup):
+        one()
+    t_enc = t_step = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        a, b = one()
+        t_enc += a
+        t_step += b
+    wall = time.perf_counter() - t0
+    t_enc /= args.steps
+    t_step /= args.steps
+    img_s = 1.0 / (t_enc + t_step * scale)
+    sample = (f"B=1 full-geometry encode ({t_enc:.2f}s) + decode step 0 incl. the reference's dead encoder call ({t_step:.2f}s), "
+              f"x{scale:.1f} (dense per-step FLOP model) for 50 steps; extrapolated")
+    line = {"impl": "reference", "metric": METRIC, "value": img_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "B=1 256x256 encode + 50-step decode, 512 tokens (bounded sample per step)", "batch_per_gpu": 1},
+            "cpu_baseline": {"value": img_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": img_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu(args):
+    import torch.distributed as dist
+    from selftoktokenizer_b200.capi import Engine
+    from selftoktokenizer_b200.dist import gather_tokens
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    d = C.FULL
+    B = args.batch
+    sd = synth.synth_state_dict(d, device=dev)
+    eng = Engine(d, sd, device=dev, precision=args.precision, steps=DECODE_STEPS)
+    del sd
+    torch.cuda.empty_cache()
+    x0 = synth.synth_tensor(f"bench.x0.{rank}", (B, d.in_channels, d.latent, d.latent), "emb", 1.0, device=dev)
+    noise = synth.synth_tensor(f"bench.noise.{rank}", (B, d.in_channels, d.latent, d.latent), "emb", 1.0, device=dev)
+    x0_h, noise_h = x0.cpu().pin_memory(), noise.cpu().pin_memory()
+    tok_h = torch.empty(B, d.K, dtype=torch.int64).pin_memory()
+    out_h = torch.empty_like(noise_h).pin_memory()
+
+    def step_device():
+        tok = eng.encode(x0)
+        n = eng.last_launch_count
+        if world > 1:
+            gather_tokens(tok, B * world)           # the path's only exchange: [B,512] int64 per rank over NVLink
+        eng.decode(tok, noise)
+        return n + eng.last_launch_count
+
+    def step_host():
+        eng.encode_host(x0_h, tok_h)
+        if world > 1:
+            gather_tokens(tok_h.to(dev, non_blocking=True), B * world)
+        eng.decode_host(tok_h, noise_h, out_h)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launches = 0
+        for _ in range(steps):
+            r = fn()
+            launches += r or 0
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    value = B * world * args.steps / (ms / 1000.0)
+    # ---- end to end through the host-buffer entry points
+    step_host()
+    ms_h, _ = timed(step_host, args.steps)
+    e2e = B * world * args.steps / (ms_h / 1000.0)
+    h2d = x0_h.numel() * 4 + tok_h.numel() * 8 + noise_h.numel() * 4
+    d2h = tok_h.numel() * 8 + out_h.numel() * 4
+    # ---- roofline of the dominant kernel class: one profiled (graph-off, event-bracketed) step
+    roof = None
+    prof = {}
+    if rank == 0:
+        eng.set_use_graph(False)
+        eng.set_profile(True)
+        tok = eng.encode(x0)
+        eng.decode(tok, noise)
+        prof = eng.get_profile()
+        eng.set_profile(False)
+        eng.set_use_graph(True)
+        pk = peaks()
+        total_ms = sum(v[0] for v in prof.values())
+        if "gemm_tcgen05" in prof:
+            g_ms, g_n = prof["gemm_tcgen05"]
+            flops = gemm_flops_per_step(B)
+            ach = flops / (g_ms / 1000.0) / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::f16, %s)" % args.precision,
+                    "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                    "traffic": None, "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
+                    "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,
+                    "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs)"}
+    # ---- CPU baseline (oracle port on the host cores), rank 0 at N=1 only
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        eng.close()
+        torch.cuda.empty_cache()
+        one, scale = cpu_sample(os.cpu_count())
+        t_enc, t_step = one()
+        v = 1.0 / (t_enc + t_step * scale)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"B=1 full-geometry encode ({t_enc:.2f}s) + decode step 0 incl. the reference's dead encoder call "
+                         f"({t_step:.2f}s), x{scale:.1f} dense per-step FLOP model for 50 steps; extrapolated"}
+    if rank == 0:
+        eff, dense = S.decode_flops_per_image(d.K, d.stages, d.k_per_stage, DECODE_STEPS, d.dit_depth, d.n_img)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate; encoder/VQ fp32)",
+                          "bf16": "bf16 (tcgen05, fp32 accumulate; encoder/VQ fp32)", "fp32": "f32"}[args.precision],
+                "data": "synthetic",
+                "config": {"workload": f"batch={B}/GPU 256x256 encode + 50-step diffusion decode (512 tokens, no VAE/renderer)",
+                           "batch_per_gpu": B, "global_batch": B * world, "decode_steps": DECODE_STEPS, "precision": args.precision,
+                           "parallelism": f"dp{world} (images sharded, weights replicated, 1 NCCL all-gather of tokens/step)",
+                           "l2": "working set >> L2: 16.7 GB of weight planes + ~3 GB activations streamed per DiT step",
+                           "algorithmic_tflop_per_image": eff / 1e12},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_h / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "kernel_classes_ms": {k: round(v[0], 3) for k, v in prof.items()},
+                "kernel_classes_launches": {k: v[1] for k, v in prof.items()}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("SELFTOK_PRECISION", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the selftok_b200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arithmetic)")
+    if args.gpus > 1 and "RANK" not in os.environ:
+        raise SystemExit("launch multi-GPU runs with: python -m torch.distributed.run --nnodes=1 --nproc-per-node N "
+                         "--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...")
+    run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

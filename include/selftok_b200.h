@@ -140,6 +140,12 @@ int64_t selftok_device_bytes(selftok_handle_t h);
 /* Enable (1) / disable (0) CUDA-graph capture of the decode loop (default 1). */
 int selftok_set_use_graph(selftok_handle_t h, int enable);
 
+/* Per-kernel-class device timing: with profiling on (and graphs off) every launch of a hot-path call is bracketed
+ * by CUDA events on its stream.  selftok_get_profile synchronises, writes the summed milliseconds and launch counts
+ * of the 8 classes (0 tcgen05 GEMM, 1 attention, 2 LayerNorm+modulate, 3 fp32 FFMA linear, 4 VQ, 5 other) and resets. */
+int selftok_set_profile(selftok_handle_t h, int enable);
+int selftok_get_profile(selftok_handle_t h, double* ms_out /*[8]*/, int64_t* count_out /*[8]*/);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks call these through the same ABI) ---------- */
 /* y[M,N] = act(A[M,K] W[N,K]^T + bias) (+ epilogue), fp32 FFMA.  act: 0 none, 1 gelu-tanh, 2 silu. */
 int selftok_k_linear_f32(const float* A_dev, const float* W_dev, const float* bias_dev, float* out_dev,

@@ -25,7 +25,7 @@ SYMBOLS = [
     "selftok_set_schedule", "selftok_finalize", "selftok_encode", "selftok_vq_argmax", "selftok_lookup",
     "selftok_decode", "selftok_dit_velocity", "selftok_render", "selftok_encode_host", "selftok_decode_host",
     "selftok_render_host", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
-    "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
+    "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
     "selftok_k_attention_tc",
 ]
 
@@ -76,6 +76,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.selftok_device_bytes.argtypes = [vp]
     lib.selftok_device_bytes.restype = i64
     lib.selftok_set_use_graph.argtypes = [vp, i32]
+    lib.selftok_set_profile.argtypes = [vp, i32]
+    lib.selftok_get_profile.argtypes = [vp, vp, vp]
     lib.selftok_k_linear_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
     lib.selftok_k_linear_tc.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
     lib.selftok_k_ln_mod_f32.argtypes = [vp, vp, vp, i64, i32, vp, i64, i32, vp]
@@ -248,6 +250,18 @@ class Engine:
     # ------------------------------------------------------------------ misc
     def set_use_graph(self, enable: bool) -> None:
         check(self.lib.selftok_set_use_graph(self.h, int(enable)))
+
+    PROFILE_CLASSES = ("gemm_tcgen05", "attention", "ln_modulate", "linear_f32", "vq", "other", "_6", "_7")
+
+    def set_profile(self, enable: bool) -> None:
+        check(self.lib.selftok_set_profile(self.h, int(enable)))
+
+    def get_profile(self):
+        """-> {class: (milliseconds, launches)} since the last call (synchronises the device)."""
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        check(self.lib.selftok_get_profile(self.h, ms, cnt))
+        return {n: (ms[i], int(cnt[i])) for i, n in enumerate(self.PROFILE_CLASSES) if cnt[i]}
 
     @property
     def last_launch_count(self) -> int:

@@ -75,7 +75,31 @@ struct selftok_engine {
   EncodeWs ews;
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (B, steps) -> (exec, launches)
   int64_t last_launches = 0;
+  // optional per-kernel-class timing (CUDA events around every launch; only meaningful with graphs disabled)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;     // pairs (start, stop)
+  std::vector<int> prof_cat;
 };
+
+enum ProfCat { PC_GEMM_TC = 0, PC_ATTN = 1, PC_LN = 2, PC_LINEAR_F32 = 3, PC_VQ = 4, PC_OTHER = 5, PC_COUNT = 8 };
+struct ProfScope {
+  selftok_engine* e; cudaStream_t s; bool on;
+  ProfScope(selftok_engine* e_, int cat, cudaStream_t s_) : e(e_), s(s_), on(e_->prof_on) {
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    e->prof_ev.push_back(a); e->prof_ev.push_back(b); e->prof_cat.push_back(cat);
+    cudaEventRecord(a, s);
+  }
+  void end() { if (on) cudaEventRecord(e->prof_ev.back(), s); }
+};
+#define PROF(cat, expr)                         \
+  do {                                          \
+    ProfScope _ps(e, (cat), s);                 \
+    int _st = (expr);                           \
+    _ps.end();                                  \
+    if (_st != 0) return _st;                   \
+  } while (0)
 
 static int dmalloc(selftok_engine* e, std::vector<void*>& pool, void** p, size_t bytes) {
   STK_CUDA(cudaMalloc(p, bytes ? bytes : 16));
@@ -115,7 +139,8 @@ static int lin32(selftok_engine* e, const std::string& prefix, const float* A, i
   int K = (int)(W->numel / W->shape[0]);
   ep.bias = Bv->d;
   if (ep.ldo == 0) ep.ldo = N;
-  return launch_linear_f32(A, lda, W->d, K, M, N, K, ep, s);
+  PROF(PC_LINEAR_F32, launch_linear_f32(A, lda, W->d, K, M, N, K, ep, s));
+  return 0;
 }
 // tcgen05 path: A given as bf16 planes
 static int lintc(selftok_engine* e, const std::string& prefix, const bf16* A_hi, const bf16* A_lo, int64_t M,
@@ -128,7 +153,8 @@ static int lintc(selftok_engine* e, const std::string& prefix, const bf16* A_hi,
   int K = (int)(W->numel / W->shape[0]);
   ep.bias = Bv->d;
   if (ep.ldo == 0) ep.ldo = N;
-  return launch_gemm_tc(A_hi, A_lo, it->second.hi, it->second.lo, M, N, K, nsplit(e), ep, s);
+  PROF(PC_GEMM_TC, launch_gemm_tc(A_hi, A_lo, it->second.hi, it->second.lo, M, N, K, nsplit(e), ep, s));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI: lifetime
@@ -267,11 +293,11 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
     STK_CHECK(pe->numel == (int64_t)c.enc_pos_max * c.enc_pos_max * c.enc_hidden, SELFTOK_ERR_BAD_ARG, "encoder.pos_embed shape");
     int g = c.latent / c.enc_patch;
     STK_TRY(dalloc(e, e->allocs, &e->enc_pos, (int64_t)g * g * c.enc_hidden));
-    STK_TRY(launch_crop_pos(pe->d, e->enc_pos, c.enc_pos_max, g, c.enc_hidden, s));
+    PROF(PC_OTHER, launch_crop_pos(pe->d, e->enc_pos, c.enc_pos_max, g, c.enc_hidden, s));
     GETW(cb, "encoder.quantizer._codebook.embed");
     STK_CHECK(cb->numel == (int64_t)c.codebook_size * c.code_dim, SELFTOK_ERR_BAD_ARG, "codebook shape");
     STK_TRY(dalloc(e, e->allocs, &e->cbt, cb->numel));
-    STK_TRY(launch_transpose(cb->d, e->cbt, c.codebook_size, c.code_dim, s));
+    PROF(PC_OTHER, launch_transpose(cb->d, e->cbt, c.codebook_size, c.code_dim, s));
   }
   // ---- decoder tables
   STK_TRY(dalloc(e, e->allocs, &e->ctx_mod, (int64_t)(L - 1 > 0 ? L - 1 : 1) * K * 6 * D));
@@ -310,14 +336,14 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
     float* tmp;
     STK_TRY(dalloc(e, scratch, &tmp, (int64_t)e->Nimg * D));
     STK_TRY(dalloc(e, e->allocs, &e->rend_x0, (int64_t)e->Nimg * D));
-    STK_TRY(launch_bcast_rows(mt->d, nullptr, tmp, e->Nimg, 1, D, s));
-    STK_TRY(launch_bcast_rows(tmp, pe->d, e->rend_x0, 1, e->Nimg, D, s));
+    PROF(PC_OTHER, launch_bcast_rows(mt->d, nullptr, tmp, e->Nimg, 1, D, s));
+    PROF(PC_OTHER, launch_bcast_rows(tmp, pe->d, e->rend_x0, 1, e->Nimg, D, s));
   } else {
     GETW(pe, "model.pos_embed");
     STK_CHECK(pe->numel == (int64_t)c.dit_pos_max * c.dit_pos_max * D, SELFTOK_ERR_BAD_ARG, "model.pos_embed shape");
     int g = c.latent / c.dit_patch;
     STK_TRY(dalloc(e, e->allocs, &e->dit_pos, (int64_t)g * g * D));
-    STK_TRY(launch_crop_pos(pe->d, e->dit_pos, c.dit_pos_max, g, D, s));
+    PROF(PC_OTHER, launch_crop_pos(pe->d, e->dit_pos, c.dit_pos_max, g, D, s));
   }
   // ---- tensor-core operand planes of the MMDiT linears
   if (tc_mode(e)) {
@@ -332,7 +358,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
           WPack p;
           STK_TRY(dalloc(e, e->allocs, &p.hi, W->numel));
           if (nsplit(e) == 3) STK_TRY(dalloc(e, e->allocs, &p.lo, W->numel));
-          STK_TRY(launch_split_bf16(W->d, p.hi, p.lo, W->numel, s));
+          PROF(PC_OTHER, launch_split_bf16(W->d, p.hi, p.lo, W->numel, s));
           e->wp[name] = p;
         }
   }
@@ -376,38 +402,38 @@ static int encoder_features(selftok_engine* e, const float* x0, int B, cudaStrea
   const int Ni = e->Nenc, K = c.K, Hh = c.enc_hidden, Q = c.enc_qdim;
   const int64_t Mx = (int64_t)B * Ni, Mq = (int64_t)B * K;
   const float eps = 1e-6f;
-  STK_TRY(launch_patchify(x0, w.patch, B, c.in_channels, c.latent, c.latent, c.enc_patch, s));
+  PROF(PC_OTHER, launch_patchify(x0, w.patch, B, c.in_channels, c.latent, c.latent, c.enc_patch, s));
   {
     Epilogue ep;
     ep.out = w.x; ep.addtab = e->enc_pos; ep.add_ld = Hh; ep.add_period = Ni;
     STK_TRY(lin32(e, "encoder.x_embedder.proj", w.patch, c.in_channels * c.enc_patch * c.enc_patch, Mx, ep, s));
     GETW(qt, "encoder.query_tokens");
     STK_CHECK(qt->numel == (int64_t)K * Q, SELFTOK_ERR_BAD_ARG, "query_tokens shape");
-    STK_TRY(launch_bcast_rows(qt->d, nullptr, w.q, B, K, Q, s));
+    PROF(PC_OTHER, launch_bcast_rows(qt->d, nullptr, w.q, B, K, Q, s));
   }
   for (int i = 0; i < c.enc_depth; ++i) {
     const std::string p = "encoder.blocks." + std::to_string(i) + ".";
     const float* mod = e->enc_mod + (int64_t)i * K * 6 * Q;     // [K][shift_msa|scale_msa|gate_msa|shift_mlp|scale_mlp|gate_mlp]
-    STK_TRY(launch_ln_mod(w.x, Hh, nullptr, nullptr, 0, 1, w.xn, nullptr, nullptr, Hh, Mx, Hh, eps, s));
-    STK_TRY(launch_ln_mod(w.q, Q, mod, mod + Q, 6 * Q, K, w.qn, nullptr, nullptr, Q, Mq, Q, eps, s));
+    PROF(PC_LN, launch_ln_mod(w.x, Hh, nullptr, nullptr, 0, 1, w.xn, nullptr, nullptr, Hh, Mx, Hh, eps, s));
+    PROF(PC_LN, launch_ln_mod(w.q, Q, mod, mod + Q, 6 * Q, K, w.qn, nullptr, nullptr, Q, Mq, Q, eps, s));
     Epilogue ep;
     ep.out = w.xqkv; STK_TRY(lin32(e, p + "attn.qkv", w.xn, Hh, Mx, ep, s));
     ep.out = w.xkv; STK_TRY(lin32(e, p + "attn.to_query_kv", w.xn, Hh, Mx, ep, s));
     ep.out = w.qqkv; STK_TRY(lin32(e, p + "attn.query_linear", w.qn, Q, Mq, ep, s));
     AttnOut ox;
     ox.f32_a = w.xattn; ox.split = Ni; ox.ld = Hh;
-    STK_TRY(launch_attention_f32(w.xqkv, 3 * Hh, (int64_t)Ni * 3 * Hh, w.xqkv + Hh, w.xqkv + 2 * Hh, 3 * Hh, (int64_t)Ni * 3 * Hh, Ni,
+    PROF(PC_ATTN, launch_attention_f32(w.xqkv, 3 * Hh, (int64_t)Ni * 3 * Hh, w.xqkv + Hh, w.xqkv + 2 * Hh, 3 * Hh, (int64_t)Ni * 3 * Hh, Ni,
                                  nullptr, nullptr, 0, 0, 0, ox, B, Ni, c.enc_heads, Hh / c.enc_heads, 0, 0, s));
     AttnOut oq;
     oq.f32_a = w.qattn; oq.split = K; oq.ld = Q;
-    STK_TRY(launch_attention_f32(w.qqkv, 3 * Q, (int64_t)K * 3 * Q, w.xkv, w.xkv + Q, 2 * Q, (int64_t)Ni * 2 * Q, Ni,
+    PROF(PC_ATTN, launch_attention_f32(w.qqkv, 3 * Q, (int64_t)K * 3 * Q, w.xkv, w.xkv + Q, 2 * Q, (int64_t)Ni * 2 * Q, Ni,
                                  w.qqkv + Q, w.qqkv + 2 * Q, 3 * Q, (int64_t)K * 3 * Q, K, oq, B, K, c.enc_qheads,
                                  Q / c.enc_qheads, 0, 0, s));
     // image stream: x += proj(x_attn); x += mlp(norm2(x))
     Epilogue er;
     er.mode = EPI_RESID; er.out = w.x; er.resid = w.x; er.ldo = Hh;
     STK_TRY(lin32(e, p + "attn.proj", w.xattn, Hh, Mx, er, s));
-    STK_TRY(launch_ln_mod(w.x, Hh, nullptr, nullptr, 0, 1, w.xn, nullptr, nullptr, Hh, Mx, Hh, eps, s));
+    PROF(PC_LN, launch_ln_mod(w.x, Hh, nullptr, nullptr, 0, 1, w.xn, nullptr, nullptr, Hh, Mx, Hh, eps, s));
     Epilogue eg;
     eg.act = ACT_GELU; eg.out = w.xh;
     STK_TRY(lin32(e, p + "mlp.fc1", w.xn, Hh, Mx, eg, s));
@@ -416,7 +442,7 @@ static int encoder_features(selftok_engine* e, const float* x0, int B, cudaStrea
     Epilogue eq;
     eq.mode = EPI_RESID; eq.out = w.q; eq.resid = w.q; eq.ldo = Q; eq.gate = mod + 2 * Q; eq.gate_ld = 6 * Q; eq.gate_period = K;
     STK_TRY(lin32(e, p + "attn.query_proj", w.qattn, Q, Mq, eq, s));
-    STK_TRY(launch_ln_mod(w.q, Q, mod + 3 * Q, mod + 4 * Q, 6 * Q, K, w.qn, nullptr, nullptr, Q, Mq, Q, eps, s));
+    PROF(PC_LN, launch_ln_mod(w.q, Q, mod + 3 * Q, mod + 4 * Q, 6 * Q, K, w.qn, nullptr, nullptr, Q, Mq, Q, eps, s));
     eg.out = w.qh;
     STK_TRY(lin32(e, p + "q_mlp.fc1", w.qn, Q, Mq, eg, s));
     eq.gate = mod + 5 * Q;
@@ -432,7 +458,8 @@ static int run_vq(selftok_engine* e, const float* z, int64_t R, int64_t* ids, fl
   GETW(cb, "encoder.quantizer._codebook.embed");
   GETW(lw, "encoder.final_layer_norm3.weight");
   GETW(lb, "encoder.final_layer_norm3.bias");
-  return launch_vq(z, R, c.enc_qdim, wi->d, bi->d, cb->d, e->cbt, c.codebook_size, c.code_dim, lw->d, lb->d, ids, outs_q, s);
+  PROF(PC_VQ, launch_vq(z, R, c.enc_qdim, wi->d, bi->d, cb->d, e->cbt, c.codebook_size, c.code_dim, lw->d, lb->d, ids, outs_q, s));
+  return 0;
 }
 
 #define HOT_PROLOGUE(e)                                                                  \
@@ -468,7 +495,8 @@ static int run_lookup(selftok_engine* e, const int64_t* tokens, int B, float* ou
   GETW(cb, "encoder.quantizer._codebook.embed");
   GETW(lw, "encoder.final_layer_norm3.weight");
   GETW(lb, "encoder.final_layer_norm3.bias");
-  return launch_lookup_ln3(tokens, (int64_t)B * e->cfg.K, cb->d, e->cfg.codebook_size, e->cfg.code_dim, lw->d, lb->d, outs_q, s);
+  PROF(PC_OTHER, launch_lookup_ln3(tokens, (int64_t)B * e->cfg.K, cb->d, e->cfg.codebook_size, e->cfg.code_dim, lw->d, lb->d, outs_q, s));
+  return 0;
 }
 
 extern "C" __attribute__((visibility("default"))) int selftok_lookup(selftok_handle_t e, const int64_t* tokens_dev, int B, float* outs_q_dev, void* stream) {
@@ -535,10 +563,10 @@ static int pre_attention(selftok_engine* e, const std::string& blk, const float*
   Epilogue ep;
   ep.out = w.qkv; ep.ldo = 3 * D; ep.rpb_in = rpb_in; ep.rpb_out = S; ep.row_off = row_off;
   if (!tc_mode(e)) {
-    STK_TRY(launch_ln_mod(resid, D, shift, scale, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
+    PROF(PC_LN, launch_ln_mod(resid, D, shift, scale, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
     return lin32(e, blk + "attn.qkv", a32, D, M, ep, s);
   }
-  STK_TRY(launch_ln_mod(resid, D, shift, scale, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
+  PROF(PC_LN, launch_ln_mod(resid, D, shift, scale, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
   return lintc(e, blk + "attn.qkv", a_hi, a_lo, M, ep, s);
 }
 
@@ -554,14 +582,14 @@ static int post_attention(selftok_engine* e, const std::string& blk, float* resi
   eh.act = ACT_GELU;
   if (!tc_mode(e)) {
     STK_TRY(lin32(e, blk + "attn.proj", attn32, D, M, er, s));
-    STK_TRY(launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
+    PROF(PC_LN, launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
     eh.out = h32; eh.ldo = 4 * D;
     STK_TRY(lin32(e, blk + "mlp.fc1", a32, D, M, eh, s));
     er.gate = mod + 5 * D;
     return lin32(e, blk + "mlp.fc2", h32, 4 * D, M, er, s);
   }
   STK_TRY(lintc(e, blk + "attn.proj", attn_hi, attn_lo, M, er, s));
-  STK_TRY(launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
+  PROF(PC_LN, launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
   eh.mode = EPI_SPLIT; eh.out_hi = h_hi; eh.out_lo = h_lo; eh.ldo = 4 * D;
   STK_TRY(lintc(e, blk + "mlp.fc1", a_hi, a_lo, M, eh, s));
   er.gate = mod + 5 * D;
@@ -595,11 +623,11 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
     const int ctx_rows = ctx_self ? Kc : 0, ctx_keys = ctx_self ? Kc : 0;
     if (!tc_mode(e)) {
       ao.f32_a = w.attn_c; ao.f32_b = w.attn_x;
-      STK_TRY(launch_attention_f32(w.qkv, 3 * D, (int64_t)S * 3 * D, w.qkv + D, w.qkv + 2 * D, 3 * D, (int64_t)S * 3 * D, S,
+      PROF(PC_ATTN, launch_attention_f32(w.qkv, 3 * D, (int64_t)S * 3 * D, w.qkv + D, w.qkv + 2 * D, 3 * D, (int64_t)S * 3 * D, S,
                                    nullptr, nullptr, 0, 0, 0, ao, B, S, e->H, 64, ctx_rows, ctx_keys, s));
     } else {
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
-      STK_TRY(launch_attention_tc(w.qkv, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s));
+      PROF(PC_ATTN, launch_attention_tc(w.qkv, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s));
     }
     if (!last)
       STK_TRY(post_attention(e, pc, w.ctx, Mc, cmod, 6 * D, Kc, w.attn_c, w.attn_c_hi, w.attn_c_lo, w.a_c, w.a_c_hi, w.a_c_lo,
@@ -609,7 +637,7 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
   }
   // FinalLayer (mmdit.py:641-645): fp32 FFMA (N = p*p*C = 64 columns)
   const float* fm = e->final_mod + (int64_t)step * 2 * D;
-  STK_TRY(launch_ln_mod(w.x, D, fm, fm + D, 2 * D, 1, w.a_x, nullptr, nullptr, D, Mx, D, 1e-6f, s));
+  PROF(PC_LN, launch_ln_mod(w.x, D, fm, fm + D, 2 * D, 1, w.a_x, nullptr, nullptr, D, Mx, D, 1e-6f, s));
   Epilogue ep;
   ep.out = w.o_final;
   return lin32(e, "model.final_layer.linear", w.a_x, D, Mx, ep, s);
@@ -630,11 +658,11 @@ static int dit_forward(selftok_engine* e, int B, int step, cudaStream_t s) {
   const selftok_config_t& c = e->cfg;
   DecodeWs& w = e->dws;
   const int D = e->D, N = e->Nimg, Kc = e->k[step] + 1;
-  STK_TRY(launch_patchify(w.x_lat, w.patch, B, c.in_channels, c.latent, c.latent, c.dit_patch, s));
+  PROF(PC_OTHER, launch_patchify(w.x_lat, w.patch, B, c.in_channels, c.latent, c.latent, c.dit_patch, s));
   Epilogue ep;
   ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
   STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
-  STK_TRY(launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
+  PROF(PC_OTHER, launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
   return joint_blocks(e, B, Kc, step, /*ctx_self=*/false, s);
 }
 
@@ -646,7 +674,7 @@ static int decode_body(selftok_engine* e, int B, int steps, cudaStream_t s) {
   for (int i = 0; i < steps; ++i) {
     STK_TRY(dit_forward(e, B, i, s));
     // euler_step (rectified_flow.py:301-303): x <- x - (t_i - t_{i+1}) * v, fused with unpatchify
-    STK_TRY(launch_unpatchify_axpy(w.o_final, w.x_lat, w.x_lat, e->dt[i], B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+    PROF(PC_OTHER, launch_unpatchify_axpy(w.o_final, w.x_lat, w.x_lat, e->dt[i], B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
   }
   return 0;
 }
@@ -712,7 +740,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_dit_velocity(selft
   STK_TRY(run_lookup(e, w.tokens, B, w.outs_q, s));
   STK_TRY(context_embed(e, B, s));
   STK_TRY(dit_forward(e, B, step, s));
-  STK_TRY(launch_unpatchify_axpy(w.o_final, nullptr, v_out_dev, -1.f, B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+  PROF(PC_OTHER, launch_unpatchify_axpy(w.o_final, nullptr, v_out_dev, -1.f, B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
   e->last_launches = g_launch_count - launches0;
   return SELFTOK_OK;
 }
@@ -728,10 +756,10 @@ extern "C" __attribute__((visibility("default"))) int selftok_render(selftok_han
   STK_TRY(run_lookup(e, w.tokens, B, w.outs_q, s));
   STK_TRY(context_embed(e, B, s));
   // x = mask_token + positional_embedding (mmdit.py:1518-1522); context = full K rows, context rows see context only
-  STK_TRY(launch_bcast_rows(e->rend_x0, nullptr, w.x, B, e->Nimg, e->D, s));
-  STK_TRY(launch_copy_rows(w.ctx0, (int64_t)c.K * e->D, w.ctx, (int64_t)c.K * e->D, B, (int64_t)c.K * e->D, s));
+  PROF(PC_OTHER, launch_bcast_rows(e->rend_x0, nullptr, w.x, B, e->Nimg, e->D, s));
+  PROF(PC_OTHER, launch_copy_rows(w.ctx0, (int64_t)c.K * e->D, w.ctx, (int64_t)c.K * e->D, B, (int64_t)c.K * e->D, s));
   STK_TRY(joint_blocks(e, B, c.K, 0, /*ctx_self=*/true, s));
-  STK_TRY(launch_unpatchify_axpy(w.o_final, nullptr, x0_out_dev, -1.f, B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+  PROF(PC_OTHER, launch_unpatchify_axpy(w.o_final, nullptr, x0_out_dev, -1.f, B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
   e->last_launches = g_launch_count - launches0;
   return SELFTOK_OK;
 }
@@ -780,6 +808,31 @@ extern "C" __attribute__((visibility("default"))) int selftok_render_host(selfto
   STK_TRY(selftok_render(e, w.tokens, B, w.x_lat, stream));
   STK_CUDA(cudaMemcpyAsync(x0_out_host, w.x_lat, sizeof(float) * nlat, cudaMemcpyDeviceToHost, s));
   STK_CUDA(cudaStreamSynchronize(s));
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_set_profile(selftok_handle_t e, int enable) {
+  STK_CHECK(e, SELFTOK_ERR_BAD_ARG, "null handle");
+  e->prof_on = enable != 0;
+  return SELFTOK_OK;
+}
+
+// Synchronises the device, sums the recorded event pairs per kernel class and clears them.
+extern "C" __attribute__((visibility("default"))) int selftok_get_profile(selftok_handle_t e, double* ms_out, int64_t* count_out) {
+  STK_CHECK(e && ms_out && count_out, SELFTOK_ERR_BAD_ARG, "selftok_get_profile: bad argument");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  STK_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < PC_COUNT; ++i) { ms_out[i] = 0.0; count_out[i] = 0; }
+  for (size_t i = 0; i < e->prof_cat.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->prof_ev[2 * i], e->prof_ev[2 * i + 1]);
+    ms_out[e->prof_cat[i]] += ms;
+    count_out[e->prof_cat[i]] += 1;
+    cudaEventDestroy(e->prof_ev[2 * i]);
+    cudaEventDestroy(e->prof_ev[2 * i + 1]);
+  }
+  e->prof_ev.clear();
+  e->prof_cat.clear();
   return SELFTOK_OK;
 }
 

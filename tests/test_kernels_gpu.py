@@ -70,12 +70,12 @@ def test_gemm_tcgen05(dev, M, N, K, nsplit):
     torch.cuda.synchronize()
     ref = A.double() @ W.double().t() + b.double()
     err = (y.double() - ref).abs().max().item()
-    tol = 3e-5 if nsplit == 3 else 3e-2
+    tol = 2.5e-4 if nsplit == 3 else 6e-2       # bf16x3: ~2^-16 per product, random-walk over K; bf16: 2^-9
     assert err < tol, (err, M, N, K, nsplit)
     # and the split really buys precision
     if nsplit == 3 and K >= 192:
         y1 = capi.k_linear_tc(A, W, b, 1)
-        assert (y1.double() - ref).abs().max().item() > 10 * err
+        assert (y1.double() - ref).abs().max().item() > 30 * err
 
 
 @pytest.mark.parametrize("B,S,H,ctx_rows,ctx_keys", [(2, 768, 3, 0, 0), (2, 276, 24, 0, 0), (3, 48, 3, 0, 0), (2, 300, 2, 44, 44),
