@@ -153,6 +153,8 @@ int selftok_k_linear_f32(const float* A_dev, const float* W_dev, const float* bi
 /* Same product on the tcgen05 path: A/W given as fp32, split into bf16 planes internally (nsplit 1 or 3). */
 int selftok_k_linear_tc(const float* A_dev, const float* W_dev, const float* bias_dev, float* out_dev,
                         int64_t M, int N, int K, int nsplit, void* stream);
+/* Process-wide choice of the tcgen05 GEMM variant: 2 = cta_group::2 SM-pair kernel (default), 1 = single-CTA kernel. */
+int selftok_k_set_gemm_ctas(int n);
 /* out = LN(x) * (1 + scale[m % period]) + shift[m % period], rows of D; eps 1e-6, no affine. */
 int selftok_k_ln_mod_f32(const float* x_dev, const float* shift_dev, const float* scale_dev, int64_t ld_mod,
                          int period, float* out_dev, int64_t M, int D, void* stream);

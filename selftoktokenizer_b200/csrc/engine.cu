@@ -871,6 +871,12 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_linear_tc(const 
   return st;
 }
 
+extern "C" __attribute__((visibility("default"))) int selftok_k_set_gemm_ctas(int n) {
+  STK_CHECK(n == 1 || n == 2, SELFTOK_ERR_BAD_ARG, "selftok_k_set_gemm_ctas: n must be 1 or 2");
+  gemm_tc_set_ctas(n);
+  return SELFTOK_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int selftok_k_ln_mod_f32(const float* x, const float* shift, const float* scale, int64_t ld_mod, int period,
                                     float* out, int64_t M, int D, void* stream) {
   return launch_ln_mod(x, D, shift, scale, ld_mod, period, out, nullptr, nullptr, D, M, D, 1e-6f, (cudaStream_t)stream);

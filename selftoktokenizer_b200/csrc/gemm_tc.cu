@@ -14,6 +14,7 @@
 #include "kernels.h"
 
 #include <cuda.h>   // CUtensorMap types only; the driver entry point is resolved at run time (no -lcuda)
+#include <stdlib.h>
 
 namespace stk {
 
@@ -114,6 +115,59 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 // both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
 __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// One 32-column chunk of one output row: bias, activation and the fused epilogue (store / gated residual / bf16 split).
+__device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const uint32_t (&r)[32], int n0, int N, int64_t orow,
+                                               const float* gate_row, const float* add_row) {
+  const bool full = n0 + 32 <= N;
+#pragma unroll
+  for (int j4 = 0; j4 < 8; ++j4) {
+    float y[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + j4 * 4 + j;
+      float v = __uint_as_float(r[j4 * 4 + j]);
+      if (full || n < N) {
+        if (e.bias) v += e.bias[n];
+        v = apply_act(v, e.act);
+      }
+      y[j] = v;
+    }
+    const int n = n0 + j4 * 4;
+    if (full || n + 3 < N) {
+      if (e.mode == EPI_STORE) {
+        if (add_row) { float4 a = *reinterpret_cast<const float4*>(add_row + n); y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; }
+        *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = make_float4(y[0], y[1], y[2], y[3]);
+      } else if (e.mode == EPI_RESID) {
+        float4 g = gate_row ? *reinterpret_cast<const float4*>(gate_row + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+        float4 x = *reinterpret_cast<const float4*>(e.resid + orow * e.ldo + n);
+        x.x += g.x * y[0]; x.y += g.y * y[1]; x.z += g.z * y[2]; x.w += g.w * y[3];
+        *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = x;
+      } else {
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
+        *reinterpret_cast<uint2*>(e.out_hi + orow * e.ldo + n) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+        if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + orow * e.ldo + n) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+      }
+    } else {
+      for (int j = 0; j < 4; ++j) {
+        const int nn = n + j;
+        if (nn >= N) break;
+        if (e.mode == EPI_STORE) {
+          e.out[orow * e.ldo + nn] = y[j] + (add_row ? add_row[nn] : 0.f);
+        } else if (e.mode == EPI_RESID) {
+          e.out[orow * e.ldo + nn] = e.resid[orow * e.ldo + nn] + (gate_row ? gate_row[nn] : 1.f) * y[j];
+        } else {
+          __nv_bfloat16 hh, ll;
+          split_bf16(y[j], hh, ll);
+          e.out_hi[orow * e.ldo + nn] = hh;
+          if (e.out_lo) e.out_lo[orow * e.ldo + nn] = ll;
+        }
+      }
+    }
+  }
 }
 
 struct GemmParams {
@@ -257,56 +311,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         tmem_ld_wait();
-        if (row_ok) {
-          const bool full = n0 + 32 <= p.N;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            float y[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int n = n0 + j4 * 4 + j;
-              float v = __uint_as_float(r[j4 * 4 + j]);
-              if (full || n < p.N) {
-                if (e.bias) v += e.bias[n];
-                v = apply_act(v, e.act);
-              }
-              y[j] = v;
-            }
-            const int n = n0 + j4 * 4;
-            if (full || n + 3 < p.N) {
-              if (e.mode == EPI_STORE) {
-                if (add_row) { float4 a = *reinterpret_cast<const float4*>(add_row + n); y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; }
-                *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = make_float4(y[0], y[1], y[2], y[3]);
-              } else if (e.mode == EPI_RESID) {
-                float4 g = gate_row ? *reinterpret_cast<const float4*>(gate_row + n) : make_float4(1.f, 1.f, 1.f, 1.f);
-                float4 x = *reinterpret_cast<const float4*>(e.resid + orow * e.ldo + n);
-                x.x += g.x * y[0]; x.y += g.y * y[1]; x.z += g.z * y[2]; x.w += g.w * y[3];
-                *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = x;
-              } else {
-                __nv_bfloat16 h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
-                *reinterpret_cast<uint2*>(e.out_hi + orow * e.ldo + n) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-                if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + orow * e.ldo + n) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
-              }
-            } else {
-              for (int j = 0; j < 4; ++j) {
-                const int nn = n + j;
-                if (nn >= p.N) break;
-                if (e.mode == EPI_STORE) {
-                  e.out[orow * e.ldo + nn] = y[j] + (add_row ? add_row[nn] : 0.f);
-                } else if (e.mode == EPI_RESID) {
-                  e.out[orow * e.ldo + nn] = e.resid[orow * e.ldo + nn] + (gate_row ? gate_row[nn] : 1.f) * y[j];
-                } else {
-                  __nv_bfloat16 hh, ll;
-                  split_bf16(y[j], hh, ll);
-                  e.out_hi[orow * e.ldo + nn] = hh;
-                  if (e.out_lo) e.out_lo[orow * e.ldo + nn] = ll;
-                }
-              }
-            }
-          }
-        }
+        if (row_ok) epilogue_chunk(e, r, n0, p.N, orow, gate_row, add_row);
       }
       tc_fence_before();
       __syncwarp();
@@ -322,12 +327,219 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------- 2-CTA kernel
+// cta_group::2: a cluster of two CTAs (one SM pair) computes a 256 x 256 output tile with UMMA 256x256x16.  Each CTA
+// stages its own 128 A rows and HALF of the W tile (128 of the 256 N rows); the tensor cores of the pair exchange the
+// halves, so per SM the shared-memory traffic (TMA fill + operand reads) drops from 156-192 B/clk to 104-128 B/clk and the
+// L2 -> SM bytes per FLOP halve.  Only the leader CTA (cluster rank 0) issues MMAs.
+//   full[s]    lives in the leader; both CTAs' TMA loads complete_tx on it (peer bit of the barrier address cleared)
+//   empty[s]   one per CTA; the leader's tcgen05.commit multicasts the arrive to both
+//   tfull[a]   one per CTA (multicast commit); tempty[a] lives in the leader and counts the 8 epilogue warps of the pair
+template <int NSPLIT> struct Cfg2 {
+  static constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
+  static constexpr int HALF_B_BYTES = (BN / 2) * BK * 2;                                 // 16 KiB
+  static constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + HALF_B_BYTES);             // 32 KiB / 64 KiB per CTA
+  static constexpr int STAGES = NSPLIT == 3 ? 3 : 6;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(local_bar), "r"(rank) : "memory");
+}
+
+__device__ __forceinline__ void pair_coords(int t, int pm_tiles, int n_tiles, int& pm, int& n_blk) {
+  constexpr int GM = 4;                                   // 4 pair-rows = 1024 A rows share each W tile in L2
+  const int per_group = GM * n_tiles;
+  const int group = t / per_group;
+  const int first = group * GM;
+  const int gm = min(GM, pm_tiles - first);
+  const int local = t - group * per_group;
+  pm = first + local % gm;
+  n_blk = local / gm;
+}
+
+template <int NSPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const GemmParams p) {
+  using C = Cfg2<NSPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pm_tiles = (int)((p.M + 2 * BM - 1) / (2 * BM)), n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = pm_tiles * n_tiles;
+  const int nk = (p.K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a_hi);
+    tma_prefetch_desc(&map_b_hi);
+    if (NSPLIT == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                     // peer barriers initialised before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int pm, n_blk;
+        pair_coords(t, pm_tiles, n_tiles, pm, n_blk);
+        const int m_row = pm * 2 * BM + (int)rank * BM;            // this CTA's 128 A rows
+        const int n_row = n_blk * BN + (int)rank * (BN / 2);       // this CTA's half of the W tile
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t fb = full_bar(stage) & 0xFEFFFFFFu;       // leader's barrier (peer bit cleared)
+          if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
+          tma_load_2d_2sm(sa, &map_a_hi, fb, kb * BK, m_row);
+          tma_load_2d_2sm(sa + C::PLANES * A_TILE_BYTES, &map_b_hi, fb, kb * BK, n_row);
+          if (NSPLIT == 3) {
+            tma_load_2d_2sm(sa + A_TILE_BYTES, &map_a_lo, fb, kb * BK, m_row);
+            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + C::HALF_B_BYTES, &map_b_lo, fb, kb * BK, n_row);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer (leader CTA only)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa_hi = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb_hi = sa_hi + C::PLANES * A_TILE_BYTES;
+          const uint32_t sa_lo = sa_hi + A_TILE_BYTES;
+          const uint32_t sb_lo = sb_hi + C::HALF_B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 2;
+            const uint64_t da_hi = make_smem_desc(sa_hi + koff), db_hi = make_smem_desc(sb_hi + koff);
+            tc_mma_f16_2sm(d_tmem, da_hi, db_hi, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (NSPLIT == 3) {
+              const uint64_t da_lo = make_smem_desc(sa_lo + koff), db_lo = make_smem_desc(sb_lo + koff);
+              tc_mma_f16_2sm(d_tmem, da_hi, db_lo, idesc, 1u);
+              tc_mma_f16_2sm(d_tmem, da_lo, db_hi, idesc, 1u);
+            }
+          }
+          tc_commit_mc2(empty_bar(stage));                         // frees the slot in BOTH CTAs
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_mc2(tfull_bar(acc));                             // accumulator ready in BOTH CTAs
+      }
+    }
+  } else {
+    // =========================================================== epilogue warps 2..5 of both CTAs
+    const int quarter = warp & 3;
+    const Epilogue& e = p.ep;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      int pm, n_blk;
+      pair_coords(t, pm_tiles, n_tiles, pm, n_blk);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t m = (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      int64_t orow = m;
+      if (e.rpb_in > 0) orow = (m / e.rpb_in) * e.rpb_out + e.row_off + (m % e.rpb_in);
+      const float* gate_row = (e.mode == EPI_RESID && e.gate) ? e.gate + (m % e.gate_period) * e.gate_ld : nullptr;
+      const float* add_row = (e.mode == EPI_STORE && e.addtab) ? e.addtab + (m % e.add_period) * e.add_ld : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_blk * BN + c * 32;
+        if (n0 >= p.N) break;
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        if (row_ok) epilogue_chunk(e, r, n0, p.N, orow, gate_row, add_row);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's barrier counts all 8 epilogue warps
+    }
+  }
+  // ---- teardown: nobody may exit (or free TMEM) while the peer can still touch its barriers / shared memory
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
+int g_gemm_ctas = 2;      // 2: cta_group::2 pair kernel (default); 1: single-CTA kernel (SELFTOK_GEMM_CTAS=1)
 
 int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, int box_rows) {
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
@@ -346,6 +558,8 @@ int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, in
 
 }  // namespace
 
+void gemm_tc_set_ctas(int n) { g_gemm_ctas = n == 1 ? 1 : 2; }
+
 int gemm_tc_init() {
   if (g_encode) return 0;
   void* fn = nullptr;
@@ -357,6 +571,10 @@ int gemm_tc_init() {
   STK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   STK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
   STK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES));
+  STK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::SMEM_BYTES));
+  STK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<3>::SMEM_BYTES));
+  const char* v = getenv("SELFTOK_GEMM_CTAS");
+  if (v) g_gemm_ctas = atoi(v) == 1 ? 1 : 2;
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   return 0;
 }
@@ -371,16 +589,29 @@ int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const _
   STK_CHECK(ep.ldo % 4 == 0 && N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");
   STK_CHECK(ep.mode != EPI_RESID || ep.gate == nullptr || ep.gate_ld % 4 == 0, -2, "gemm_tc: gate pitch must be a multiple of 4");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+  const bool pair = g_gemm_ctas == 2 && g_num_sms >= 2;
+  const int b_box = pair ? BN / 2 : BN;
   STK_TRY(make_map(&ma_hi, A_hi, M, K, BM));
-  STK_TRY(make_map(&mb_hi, W_hi, N, K, BN));
+  STK_TRY(make_map(&mb_hi, W_hi, N, K, b_box));
   if (nsplit == 3) {
     STK_TRY(make_map(&ma_lo, A_lo, M, K, BM));
-    STK_TRY(make_map(&mb_lo, W_lo, N, K, BN));
+    STK_TRY(make_map(&mb_lo, W_lo, N, K, b_box));
   } else {
     ma_lo = ma_hi; mb_lo = mb_hi;
   }
   GemmParams p{M, N, K, ep};
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
+  if (pair) {
+    const int pairs = (int)((M + 2 * BM - 1) / (2 * BM)) * n_tiles;
+    const int clusters = pairs < g_num_sms / 2 ? pairs : g_num_sms / 2;
+    if (nsplit == 3)
+      gemm_tc2_kernel<3><<<2 * clusters, NUM_THREADS, Cfg2<3>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    else
+      gemm_tc2_kernel<1><<<2 * clusters, NUM_THREADS, Cfg2<1>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    count_launch();
+    STK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int tiles = m_tiles * n_tiles;
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
   if (nsplit == 3)

@@ -77,6 +77,7 @@ int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const _
                    const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
                    cudaStream_t s);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes; idempotent
+void gemm_tc_set_ctas(int n);   // 2 (default): cta_group::2 pair kernel; 1: single-CTA kernel
 
 // ---- tensor-core attention (attn_tc.cu) ------------------------------------------------------------------------
 // qkv: packed fp32 [B,S,3,H,64]

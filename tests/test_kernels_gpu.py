@@ -60,11 +60,14 @@ def test_attention_f32(dev, B, Sq, S1, S2, H, hd):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 192), (1000, 576, 192), (4096, 1536, 1536), (48, 192, 768),
-                                    (333, 4608, 1536), (2048, 6144, 1536), (1024, 1536, 6144), (129, 260, 128)])
+                                    (333, 4608, 1536), (2048, 6144, 1536), (1024, 1536, 6144), (129, 260, 128), (257, 256, 64), (1280, 4608, 1536)])
 @pytest.mark.parametrize("nsplit", [3, 1])
-def test_gemm_tcgen05(dev, M, N, K, nsplit):
-    """tcgen05 GEMM (TMA + TMEM) vs fp64.  bf16x3 must be fp32-faithful; single-pass bf16 within bf16 rounding."""
+@pytest.mark.parametrize("ctas", [2, 1])
+def test_gemm_tcgen05(dev, M, N, K, nsplit, ctas):
+    """tcgen05 GEMM (TMA + TMEM) vs fp64, both the cta_group::2 SM-pair kernel and the single-CTA kernel.
+    bf16x3 must be fp32-faithful; single-pass bf16 within bf16 rounding."""
     from selftoktokenizer_b200 import capi
+    capi.k_set_gemm_ctas(ctas)
     A, W, b = _rand((M, K), 12, dev), _rand((N, K), 13, dev, 1 / math.sqrt(K)), _rand((N,), 14, dev)
     y = capi.k_linear_tc(A, W, b, nsplit)
     torch.cuda.synchronize()
@@ -76,6 +79,7 @@ def test_gemm_tcgen05(dev, M, N, K, nsplit):
     if nsplit == 3 and K >= 192:
         y1 = capi.k_linear_tc(A, W, b, 1)
         assert (y1.double() - ref).abs().max().item() > 30 * err
+    capi.k_set_gemm_ctas(2)
 
 
 @pytest.mark.parametrize("B,S,H,ctx_rows,ctx_keys", [(2, 768, 3, 0, 0), (2, 276, 24, 0, 0), (3, 48, 3, 0, 0), (2, 300, 2, 44, 44),
