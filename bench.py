@@ -282,6 +282,7 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": {"bf16x3": "bf16x3 (split-bf16 tcgen05, fp32 accumulate; encoder/VQ fp32)",
+                          "fp16": "fp16 (IEEE-half operands on tcgen05, fp32 accumulate; encoder/VQ/tables fp32)",
                           "bf16": "bf16 (tcgen05, fp32 accumulate; encoder/VQ fp32)", "fp32": "f32"}[args.precision],
                 "data": "synthetic",
                 "config": {"workload": f"batch={B}/GPU 256x256 encode + 50-step diffusion decode (512 tokens, no VAE/renderer)",
@@ -305,7 +306,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SELFTOK_PRECISION", "bf16x3"), choices=["bf16x3", "bf16", "fp32"])
+    ap.add_argument("--precision", default=os.environ.get("SELFTOK_PRECISION", "fp16"), choices=["bf16x3", "fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()

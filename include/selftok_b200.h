@@ -58,7 +58,8 @@ typedef enum selftok_status {
 typedef enum selftok_precision {
   SELFTOK_PREC_FP32_SIMT = 0,     /* fp32 FFMA GEMMs + fp32 attention (bring-up / bisecting reference)       */
   SELFTOK_PREC_BF16X3 = 1,        /* tcgen05 kind::f16: a_hi*b_hi + a_hi*b_lo + a_lo*b_hi, fp32 accumulate   */
-  SELFTOK_PREC_BF16 = 2           /* tcgen05 kind::f16 single pass (bf16 operands, fp32 accumulate)          */
+  SELFTOK_PREC_BF16 = 2,          /* tcgen05 kind::f16 single pass (bf16 operands, fp32 accumulate)          */
+  SELFTOK_PREC_FP16 = 3           /* tcgen05 kind::f16 single pass (IEEE half operands, fp32 accumulate)     */
 } selftok_precision;
 
 /* Flat view of cfg.tokenizer.params (configs/res256/256-eval.yml:48-105) after the reference's registries
@@ -150,7 +151,8 @@ int selftok_get_profile(selftok_handle_t h, double* ms_out /*[8]*/, int64_t* cou
 /* y[M,N] = act(A[M,K] W[N,K]^T + bias) (+ epilogue), fp32 FFMA.  act: 0 none, 1 gelu-tanh, 2 silu. */
 int selftok_k_linear_f32(const float* A_dev, const float* W_dev, const float* bias_dev, float* out_dev,
                          int64_t M, int N, int K, int act, void* stream);
-/* Same product on the tcgen05 path: A/W given as fp32, split into bf16 planes internally (nsplit 1 or 3). */
+/* Same product on the tcgen05 path: A/W given as fp32, converted to 16-bit planes internally
+ * (nsplit 3: bf16 hi+lo split, 1: bf16, 0: IEEE half single pass). */
 int selftok_k_linear_tc(const float* A_dev, const float* W_dev, const float* bias_dev, float* out_dev,
                         int64_t M, int N, int K, int nsplit, void* stream);
 /* Process-wide choice of the tcgen05 GEMM variant: 2 = cta_group::2 SM-pair kernel (default), 1 = single-CTA kernel. */
@@ -164,7 +166,8 @@ int selftok_k_attention_f32(const float* q_dev, int64_t q_ld, const float* k1_de
                             int S1, const float* k2_dev, const float* v2_dev, int64_t kv2_ld, int S2,
                             float* out_dev, int64_t out_ld, int B, int Sq, int H, int hd, void* stream);
 /* Tensor-core (bf16x3 / bf16) attention over a packed qkv buffer [B,S,3,H,64]; ctx_rows = number of leading rows
- * whose queries may only see the first `ctx_keys` keys (renderer rule; pass 0 for plain dense attention). */
+ * whose queries may only see the first `ctx_keys` keys (renderer rule; pass 0 for plain dense attention).
+ * nsplit 3: bf16 hi+lo split, 1: bf16, 0: IEEE half single pass. */
 int selftok_k_attention_tc(const float* qkv_dev, float* out_dev, int B, int S, int H, int nsplit,
                            int ctx_rows, int ctx_keys, void* stream);
 

@@ -17,7 +17,7 @@ from . import schedule as sched
 from .config import SelftokDims
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libselftok_b200.so")
-PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16": 3}
 
 # every symbol include/selftok_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
@@ -107,7 +107,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class Engine:
     """One handle (`selftok_handle_t`) on one device: weights, static tables, workspaces, CUDA graphs."""
 
-    def __init__(self, dims: SelftokDims, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "bf16x3",
+    def __init__(self, dims: SelftokDims, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "fp16",
                  steps: int = 50, start: float = 1.0):
         self.lib = load_library()
         if not torch.cuda.is_available():

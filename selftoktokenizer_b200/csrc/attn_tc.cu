@@ -17,23 +17,31 @@ namespace {
 
 constexpr int HD = 64, BQ = 64, BKV = 64, PITCH = 72;   // bf16 elements per smem row (64 + 8 pad -> conflict-free fragments)
 
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+template <int FP16>
+__device__ __forceinline__ void mma_16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (FP16)
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+template <int FP16>
 __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat16 hx, lx, hy, ly;
-  split_bf16(x, hx, lx);
-  split_bf16(y, hy, ly);
-  hi = pack_bf16x2(hx, hy);
-  lo = pack_bf16x2(lx, ly);
+  uint16_t hx, lx, hy, ly;
+  split16(x, FP16 != 0, hx, lx);
+  split16(y, FP16 != 0, hy, ly);
+  hi = hx | ((uint32_t)hy << 16);
+  lo = lx | ((uint32_t)ly << 16);
 }
 
 struct AttnTcParams {
@@ -43,7 +51,7 @@ struct AttnTcParams {
   float scale_log2e;
 };
 
-template <int NSPLIT>
+template <int NSPLIT, int FP16>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p) {
   __shared__ __align__(16) __nv_bfloat16 Ks[2][BKV][PITCH];     // [hi/lo][key][d]
   __shared__ __align__(16) __nv_bfloat16 Vs[2][BKV][PITCH];     // [hi/lo][key][d]  (B fragments via ldmatrix.trans)
@@ -63,10 +71,10 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
     float2 x10 = r1 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r1 * row_stride + d0) : z;
     float2 x01 = r0 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r0 * row_stride + d0 + 8) : z;
     float2 x11 = r1 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r1 * row_stride + d0 + 8) : z;
-    split2(x00.x, x00.y, qh[kk][0], ql[kk][0]);
-    split2(x10.x, x10.y, qh[kk][1], ql[kk][1]);
-    split2(x01.x, x01.y, qh[kk][2], ql[kk][2]);
-    split2(x11.x, x11.y, qh[kk][3], ql[kk][3]);
+    split2<FP16>(x00.x, x00.y, qh[kk][0], ql[kk][0]);
+    split2<FP16>(x10.x, x10.y, qh[kk][1], ql[kk][1]);
+    split2<FP16>(x01.x, x01.y, qh[kk][2], ql[kk][2]);
+    split2<FP16>(x11.x, x11.y, qh[kk][3], ql[kk][3]);
   }
   float o[8][4];
 #pragma unroll
@@ -88,12 +96,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
         vv = *reinterpret_cast<const float4*>(rp + (int64_t)2 * p.H * HD);
       }
       uint32_t h01, l01, h23, l23;
-      split2(kv.x, kv.y, h01, l01);
-      split2(kv.z, kv.w, h23, l23);
+      split2<FP16>(kv.x, kv.y, h01, l01);
+      split2<FP16>(kv.z, kv.w, h23, l23);
       *reinterpret_cast<uint2*>(&Ks[0][key][d4]) = make_uint2(h01, h23);
       if (NSPLIT == 3) *reinterpret_cast<uint2*>(&Ks[1][key][d4]) = make_uint2(l01, l23);
-      split2(vv.x, vv.y, h01, l01);
-      split2(vv.z, vv.w, h23, l23);
+      split2<FP16>(vv.x, vv.y, h01, l01);
+      split2<FP16>(vv.z, vv.w, h23, l23);
       *reinterpret_cast<uint2*>(&Vs[0][key][d4]) = make_uint2(h01, h23);
       if (NSPLIT == 3) *reinterpret_cast<uint2*>(&Vs[1][key][d4]) = make_uint2(l01, l23);
     }
@@ -108,12 +116,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
       for (int n = 0; n < 8; ++n) {
         const __nv_bfloat16* kr = &Ks[0][n * 8 + g][kk * 16 + tig * 2];
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr), b1 = *reinterpret_cast<const uint32_t*>(kr + 8);
-        mma_bf16(sc[n], qh[kk], b0, b1);
+        mma_16<FP16>(sc[n], qh[kk], b0, b1);
         if (NSPLIT == 3) {
           const __nv_bfloat16* kl = &Ks[1][n * 8 + g][kk * 16 + tig * 2];
           const uint32_t c0 = *reinterpret_cast<const uint32_t*>(kl), c1 = *reinterpret_cast<const uint32_t*>(kl + 8);
-          mma_bf16(sc[n], qh[kk], c0, c1);
-          mma_bf16(sc[n], ql[kk], b0, b1);
+          mma_16<FP16>(sc[n], qh[kk], c0, c1);
+          mma_16<FP16>(sc[n], ql[kk], b0, b1);
         }
       }
     }
@@ -159,10 +167,10 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t ph[4], pl[4];
-      split2(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl[0]);
-      split2(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl[1]);
-      split2(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl[2]);
-      split2(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl[3]);
+      split2<FP16>(sc[2 * kk][0], sc[2 * kk][1], ph[0], pl[0]);
+      split2<FP16>(sc[2 * kk][2], sc[2 * kk][3], ph[1], pl[1]);
+      split2<FP16>(sc[2 * kk + 1][0], sc[2 * kk + 1][1], ph[2], pl[2]);
+      split2<FP16>(sc[2 * kk + 1][2], sc[2 * kk + 1][3], ph[3], pl[3]);
       // V is row-major [key][d]; ldmatrix.trans hands each thread (k = key pair, n = d) fragments for two d-tiles at once:
       // lanes 0-7 / 8-15 address keys kk*16 + 0..7 / 8..15 of d-tile n, lanes 16-23 / 24-31 the same keys of d-tile n+1.
       const int lrow = kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
@@ -171,15 +179,15 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
         const int lcol = (n + (lane >> 4)) * 8;
         uint32_t b[4];
         ldmatrix_x4_trans(b, &Vs[0][lrow][lcol]);
-        mma_bf16(o[n], ph, b[0], b[1]);
-        mma_bf16(o[n + 1], ph, b[2], b[3]);
+        mma_16<FP16>(o[n], ph, b[0], b[1]);
+        mma_16<FP16>(o[n + 1], ph, b[2], b[3]);
         if (NSPLIT == 3) {
           uint32_t c[4];
           ldmatrix_x4_trans(c, &Vs[1][lrow][lcol]);
-          mma_bf16(o[n], ph, c[0], c[1]);
-          mma_bf16(o[n + 1], ph, c[2], c[3]);
-          mma_bf16(o[n], pl, b[0], b[1]);
-          mma_bf16(o[n + 1], pl, b[2], b[3]);
+          mma_16<FP16>(o[n], ph, c[0], c[1]);
+          mma_16<FP16>(o[n + 1], ph, c[2], c[3]);
+          mma_16<FP16>(o[n], pl, b[0], b[1]);
+          mma_16<FP16>(o[n + 1], pl, b[2], b[3]);
         }
       }
     }
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
       if (of) *reinterpret_cast<float2*>(of + idx) = make_float2(y0, y1);
       if (oh) {
         uint32_t hi, lo;
-        split2(y0, y1, hi, lo);
+        split2<FP16>(y0, y1, hi, lo);
         *reinterpret_cast<uint32_t*>(oh + idx) = hi;
         if (ol) *reinterpret_cast<uint32_t*>(ol + idx) = lo;
       }
@@ -214,14 +222,16 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
 }  // namespace
 
 int launch_attention_tc(const float* qkv, int B, int S, int H, int nsplit, int ctx_rows, int ctx_keys,
-                        const AttnOut& out, cudaStream_t s) {
+                        const AttnOut& out, cudaStream_t s, int fp16) {
   STK_CHECK(qkv && B > 0 && S > 0 && H > 0, -1, "attention_tc: bad arguments");
   STK_CHECK(nsplit == 1 || nsplit == 3, -1, "attention_tc: nsplit must be 1 or 3");
   STK_CHECK(out.ld % 2 == 0, -1, "attention_tc: output pitch must be even");
   AttnTcParams p{qkv, out, S, H, ctx_rows, ctx_keys, 0.125f * 1.4426950408889634f};
   dim3 grid((S + BQ - 1) / BQ, H, B);
-  if (nsplit == 3) attention_tc_kernel<3><<<grid, 128, 0, s>>>(p);
-  else attention_tc_kernel<1><<<grid, 128, 0, s>>>(p);
+  STK_CHECK(!fp16 || nsplit == 1, -1, "attention_tc: the fp16 mode is single-pass");
+  if (nsplit == 3) attention_tc_kernel<3, 0><<<grid, 128, 0, s>>>(p);
+  else if (fp16) attention_tc_kernel<1, 1><<<grid, 128, 0, s>>>(p);
+  else attention_tc_kernel<1, 0><<<grid, 128, 0, s>>>(p);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -47,11 +48,18 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// torch.nn.GELU(approximate="tanh"): 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))
+// torch.nn.GELU(approximate="tanh"): 0.5*x*(1+tanh(u)), u = sqrt(2/pi)*(x+0.044715*x^3)
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float inner = k0 * (x + k1 * x * x * x);
   return 0.5f * x * (1.0f + tanhf(inner));
+}
+// Same function as x / (1 + exp(-2u)) with the fast exp/divide intrinsics (~1e-6 relative): used by the tensor-core
+// epilogues, whose operands are rounded to 16 bits right afterwards.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
@@ -69,6 +77,18 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// 16-bit operand planes hold either bf16 (hi [+ lo] split) or, in the single-pass fp16 mode, IEEE half values; the
+// storage type is __nv_bfloat16 in both cases (the bits are what the tensor core is told they are).
+__device__ __forceinline__ void split16(float x, bool fp16, uint16_t& hi, uint16_t& lo) {
+  if (fp16) {
+    hi = __half_as_ushort(__float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f)));   // saturate instead of overflowing to inf
+    lo = 0;
+  } else {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+  }
 }
 
 }  // namespace stk

@@ -129,6 +129,7 @@ static const Tensor* find(selftok_engine* e, const std::string& name) {
 
 static bool tc_mode(const selftok_engine* e) { return e->cfg.precision != SELFTOK_PREC_FP32_SIMT; }
 static int nsplit(const selftok_engine* e) { return e->cfg.precision == SELFTOK_PREC_BF16X3 ? 3 : 1; }
+static int is_fp16(const selftok_engine* e) { return e->cfg.precision == SELFTOK_PREC_FP16 ? 1 : 0; }
 
 // y = act(A W^T + b) with weights looked up by checkpoint prefix (fp32 FFMA path)
 static int lin32(selftok_engine* e, const std::string& prefix, const float* A, int64_t lda, int64_t M, Epilogue ep,
@@ -153,7 +154,8 @@ static int lintc(selftok_engine* e, const std::string& prefix, const bf16* A_hi,
   int K = (int)(W->numel / W->shape[0]);
   ep.bias = Bv->d;
   if (ep.ldo == 0) ep.ldo = N;
-  PROF(PC_GEMM_TC, launch_gemm_tc(A_hi, A_lo, it->second.hi, it->second.lo, M, N, K, nsplit(e), ep, s));
+  ep.fp16 = is_fp16(e);
+  PROF(PC_GEMM_TC, launch_gemm_tc(A_hi, A_lo, it->second.hi, it->second.lo, M, N, K, nsplit(e), ep, s, is_fp16(e)));
   return 0;
 }
 
@@ -182,7 +184,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_create(const selft
   int hd1 = cfg->enc_hidden / cfg->enc_heads, hd2 = cfg->enc_qdim / cfg->enc_qheads;
   STK_CHECK((hd1 == 16 || hd1 == 32 || hd1 == 64) && (hd2 == 16 || hd2 == 32 || hd2 == 64), SELFTOK_ERR_UNSUPPORTED,
             "encoder head_dim must be 16/32/64");
-  STK_CHECK(cfg->precision >= 0 && cfg->precision <= 2, SELFTOK_ERR_BAD_ARG, "bad precision");
+  STK_CHECK(cfg->precision >= 0 && cfg->precision <= 3, SELFTOK_ERR_BAD_ARG, "bad precision");
   STK_CUDA(cudaSetDevice(cfg->device));
   selftok_engine* e = new selftok_engine();
   e->cfg = *cfg;
@@ -358,7 +360,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
           WPack p;
           STK_TRY(dalloc(e, e->allocs, &p.hi, W->numel));
           if (nsplit(e) == 3) STK_TRY(dalloc(e, e->allocs, &p.lo, W->numel));
-          PROF(PC_OTHER, launch_split_bf16(W->d, p.hi, p.lo, W->numel, s));
+          PROF(PC_OTHER, launch_split_bf16(W->d, p.hi, p.lo, W->numel, s, is_fp16(e)));
           e->wp[name] = p;
         }
   }
@@ -566,7 +568,7 @@ static int pre_attention(selftok_engine* e, const std::string& blk, const float*
     PROF(PC_LN, launch_ln_mod(resid, D, shift, scale, ld_mod, period, a32, nullptr, nullptr, D, M, D, 1e-6f, s));
     return lin32(e, blk + "attn.qkv", a32, D, M, ep, s);
   }
-  PROF(PC_LN, launch_ln_mod(resid, D, shift, scale, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
+  PROF(PC_LN, launch_ln_mod(resid, D, shift, scale, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s, is_fp16(e)));
   return lintc(e, blk + "attn.qkv", a_hi, a_lo, M, ep, s);
 }
 
@@ -589,7 +591,7 @@ static int post_attention(selftok_engine* e, const std::string& blk, float* resi
     return lin32(e, blk + "mlp.fc2", h32, 4 * D, M, er, s);
   }
   STK_TRY(lintc(e, blk + "attn.proj", attn_hi, attn_lo, M, er, s));
-  PROF(PC_LN, launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s));
+  PROF(PC_LN, launch_ln_mod(resid, D, mod + 3 * D, mod + 4 * D, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s, is_fp16(e)));
   eh.mode = EPI_SPLIT; eh.out_hi = h_hi; eh.out_lo = h_lo; eh.ldo = 4 * D;
   STK_TRY(lintc(e, blk + "mlp.fc1", a_hi, a_lo, M, eh, s));
   er.gate = mod + 5 * D;
@@ -627,7 +629,8 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
                                    nullptr, nullptr, 0, 0, 0, ao, B, S, e->H, 64, ctx_rows, ctx_keys, s));
     } else {
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
-      PROF(PC_ATTN, launch_attention_tc(w.qkv, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s));
+      ao.fp16 = is_fp16(e);
+      PROF(PC_ATTN, launch_attention_tc(w.qkv, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, is_fp16(e)));
     }
     if (!last)
       STK_TRY(post_attention(e, pc, w.ctx, Mc, cmod, 6 * D, Kc, w.attn_c, w.attn_c_hi, w.attn_c_lo, w.a_c, w.a_c_hi, w.a_c_lo,
@@ -849,7 +852,9 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_linear_f32(const
 
 extern "C" __attribute__((visibility("default"))) int selftok_k_linear_tc(const float* A, const float* W, const float* bias, float* out, int64_t M, int N, int K,
                                    int ns, void* stream) {
-  STK_CHECK(A && W && out && (ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_linear_tc: bad argument");
+  STK_CHECK(A && W && out && (ns == 0 || ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_linear_tc: bad argument");
+  const int fp16 = ns == 0;
+  if (fp16) ns = 1;
   STK_TRY(gemm_tc_init());
   cudaStream_t s = (cudaStream_t)stream;
   bf16 *ah, *al = nullptr, *wh, *wl = nullptr;
@@ -859,11 +864,11 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_linear_tc(const 
     STK_CUDA(cudaMalloc(&al, sizeof(bf16) * M * K));
     STK_CUDA(cudaMalloc(&wl, sizeof(bf16) * (int64_t)N * K));
   }
-  int st = launch_split_bf16(A, ah, al, M * K, s);
-  if (!st) st = launch_split_bf16(W, wh, wl, (int64_t)N * K, s);
+  int st = launch_split_bf16(A, ah, al, M * K, s, fp16);
+  if (!st) st = launch_split_bf16(W, wh, wl, (int64_t)N * K, s, fp16);
   Epilogue ep;
   ep.bias = bias; ep.out = out; ep.ldo = N;
-  if (!st) st = launch_gemm_tc(ah, al, wh, wl, M, N, K, ns, ep, s);
+  if (!st) st = launch_gemm_tc(ah, al, wh, wl, M, N, K, ns, ep, s, fp16);
   cudaStreamSynchronize(s);
   cudaFree(ah); cudaFree(wh);
   if (al) cudaFree(al);
@@ -893,8 +898,10 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_f32(co
 
 extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(const float* qkv, float* out, int B, int S, int H, int ns, int ctx_rows, int ctx_keys,
                                       void* stream) {
-  STK_CHECK(qkv && out && (ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
+  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
+  const int fp16 = ns == 0;
+  if (fp16) ns = 1;
   AttnOut ao;
   ao.f32_a = out; ao.split = S; ao.ld = (int64_t)H * 64;
-  return launch_attention_tc(qkv, B, S, H, ns, ctx_rows, ctx_keys, ao, (cudaStream_t)stream);
+  return launch_attention_tc(qkv, B, S, H, ns, ctx_rows, ctx_keys, ao, (cudaStream_t)stream, fp16);
 }

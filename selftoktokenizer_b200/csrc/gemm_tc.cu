@@ -4,7 +4,7 @@
 //              y = A_hi W_hi^T + A_hi W_lo^T + A_lo W_hi^T, all three products accumulated into the same TMEM tile.
 //   tile       128 x 256 x 64 per pipeline stage, UMMA 128x256x16 (kind::f16, cta_group::1)
 //   staging    TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) -> shared memory ring, mbarrier full/empty pairs
-//   roles      warp 0: TMA producer (1 thread) | warp 1: MMA issuer (1 thread) | warps 2-5: epilogue (TMEM -> regs -> HBM)
+//   roles      warp 0: TMA producer (1 thread) | warp 1: MMA issuer (1 thread) | warps 2-9: epilogue (TMEM -> regs -> smem transpose -> HBM)
 //   TMEM       512 columns = 2 accumulator tiles; the epilogue of tile i overlaps the MMAs of tile i+1
 //   schedule   persistent CTAs (grid = #SMs), tiles rasterised in groups of 8 M-blocks for L2 reuse of W
 //
@@ -23,14 +23,14 @@ namespace {
 constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
 constexpr int A_TILE_BYTES = BM * BK * 2;      // 16 KiB
 constexpr int B_TILE_BYTES = BN * BK * 2;      // 32 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 64 + 8 * 32;     // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;
 
 template <int NSPLIT> struct Cfg {
   static constexpr int PLANES = NSPLIT == 3 ? 2 : 1;
   static constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + B_TILE_BYTES);     // 48 KiB / 96 KiB
   static constexpr int STAGES = NSPLIT == 3 ? 2 : 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 8 * 32 * 32 * 4 /*epilogue staging*/;
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -113,58 +113,88 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1),
 // both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;                   // F16F32Format: F16 = 0, BF16 = 1
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// One 32-column chunk of one output row: bias, activation and the fused epilogue (store / gated residual / bf16 split).
-__device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const uint32_t (&r)[32], int n0, int N, int64_t orow,
-                                               const float* gate_row, const float* add_row) {
-  const bool full = n0 + 32 <= N;
+// Epilogue of one 32-row x 128-column accumulator block (TMEM lane quarter x column half), executed by one warp;
+// 8 epilogue warps cover the 128 x 256 tile.  tcgen05.ld hands lane i row i of a 32 x 32 chunk; the chunk is transposed
+// through an XOR-swizzled shared-memory tile (conflict-free 128-bit writes and reads) so that every global access of
+// the warp covers four full 128-byte row segments (8 lanes x float4 per row).  For the gated-residual epilogue all
+// residual / gate loads of a chunk are issued BEFORE the TMEM read: one memory latency per chunk, not one per row.
+// (A lane-per-row epilogue touches 32 cache lines per instruction with nothing in flight and made the LSU, not the
+// tensor pipe, the limiter of the first version of this kernel.)
+constexpr int EPI_STAGE_FLOATS = 32 * 32;
+constexpr int EPI_WARPS = 8;
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_addr, float* stage, int lane,
+                                               int64_t m_base, int64_t M, int n_first, int N) {
+  const int rsub = lane >> 3, cq = lane & 7;            // pass k: row 4k + rsub of the chunk; this lane's 4 columns
+  const bool per_row_gate = e.mode == EPI_RESID && e.gate && e.gate_period > 1;
+  const bool per_row_add = e.mode == EPI_STORE && e.addtab;
+  int orow[8], mrow[8];
+  bool rvalid[8];
 #pragma unroll
-  for (int j4 = 0; j4 < 8; ++j4) {
-    float y[4];
+  for (int k = 0; k < 8; ++k) {
+    const int64_t m = m_base + 4 * k + rsub;
+    rvalid[k] = m < M;
+    const int mi = (int)m;
+    orow[k] = e.rpb_in > 0 ? (mi / e.rpb_in) * e.rpb_out + e.row_off + (mi % e.rpb_in) : mi;
+    mrow[k] = per_row_gate ? mi % e.gate_period : (per_row_add ? mi % e.add_period : 0);
+  }
+#pragma unroll 1
+  for (int c = 0; c < (BN / 2) / 32; ++c) {
+    const int n0 = n_first + c * 32;
+    if (n0 >= N) break;                                 // warp-uniform
+    const int n = n0 + cq * 4;
+    const bool col_ok = n < N;                          // N % 4 == 0: a float4 group is all in or all out
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 bias = (e.bias && col_ok) ? ldg4(e.bias + n) : zero4;
+    float4 res[8], gt[8];
+    if (e.mode == EPI_RESID) {
+      const float4 g0 = (e.gate && !per_row_gate && col_ok) ? ldg4(e.gate + n) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + j4 * 4 + j;
-      float v = __uint_as_float(r[j4 * 4 + j]);
-      if (full || n < N) {
-        if (e.bias) v += e.bias[n];
-        v = apply_act(v, e.act);
+      for (int k = 0; k < 8; ++k) {
+        const bool ok = col_ok && rvalid[k];
+        res[k] = ok ? ldg4(e.resid + (int64_t)orow[k] * e.ldo + n) : zero4;
+        gt[k] = (per_row_gate && ok) ? ldg4(e.gate + (int64_t)mrow[k] * e.gate_ld + n) : g0;
       }
-      y[j] = v;
     }
-    const int n = n0 + j4 * 4;
-    if (full || n + 3 < N) {
-      if (e.mode == EPI_STORE) {
-        if (add_row) { float4 a = *reinterpret_cast<const float4*>(add_row + n); y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; }
-        *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = make_float4(y[0], y[1], y[2], y[3]);
-      } else if (e.mode == EPI_RESID) {
-        float4 g = gate_row ? *reinterpret_cast<const float4*>(gate_row + n) : make_float4(1.f, 1.f, 1.f, 1.f);
-        float4 x = *reinterpret_cast<const float4*>(e.resid + orow * e.ldo + n);
-        x.x += g.x * y[0]; x.y += g.y * y[1]; x.z += g.z * y[2]; x.w += g.w * y[3];
-        *reinterpret_cast<float4*>(e.out + orow * e.ldo + n) = x;
-      } else {
-        __nv_bfloat16 h[4], l[4];
+    uint32_t r[32];
+    tmem_ld32(tmem_addr + (uint32_t)(c * 32), r);
+    tmem_ld_wait();
+    __syncwarp();                                       // previous chunk fully read back
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_bf16(y[j], h[j], l[j]);
-        *reinterpret_cast<uint2*>(e.out_hi + orow * e.ldo + n) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-        if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + orow * e.ldo + n) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<uint4*>(&stage[lane * 32 + ((q ^ (lane & 7)) << 2)]) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int row = 4 * k + rsub;
+      if (!(col_ok && rvalid[k])) continue;
+      float4 v = *reinterpret_cast<const float4*>(&stage[row * 32 + ((cq ^ (row & 7)) << 2)]);
+      float y[4] = {v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w};
+      if (e.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = gelu_tanh_fast(y[j]);
+      } else if (e.act == ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = silu(y[j]);
       }
-    } else {
-      for (int j = 0; j < 4; ++j) {
-        const int nn = n + j;
-        if (nn >= N) break;
-        if (e.mode == EPI_STORE) {
-          e.out[orow * e.ldo + nn] = y[j] + (add_row ? add_row[nn] : 0.f);
-        } else if (e.mode == EPI_RESID) {
-          e.out[orow * e.ldo + nn] = e.resid[orow * e.ldo + nn] + (gate_row ? gate_row[nn] : 1.f) * y[j];
-        } else {
-          __nv_bfloat16 hh, ll;
-          split_bf16(y[j], hh, ll);
-          e.out_hi[orow * e.ldo + nn] = hh;
-          if (e.out_lo) e.out_lo[orow * e.ldo + nn] = ll;
-        }
+      const int64_t o = (int64_t)orow[k] * e.ldo + n;
+      if (e.mode == EPI_STORE) {
+        if (per_row_add) { const float4 a = ldg4(e.addtab + (int64_t)mrow[k] * e.add_ld + n); y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; }
+        *reinterpret_cast<float4*>(e.out + o) = make_float4(y[0], y[1], y[2], y[3]);
+      } else if (e.mode == EPI_RESID) {
+        *reinterpret_cast<float4*>(e.out + o) = make_float4(res[k].x + gt[k].x * y[0], res[k].y + gt[k].y * y[1],
+                                                            res[k].z + gt[k].z * y[2], res[k].w + gt[k].w * y[3]);
+      } else {
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split16(y[j], e.fp16, h[j], l[j]);
+        *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
+        if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
       }
     }
   }
@@ -173,6 +203,7 @@ __device__ __forceinline__ void epilogue_chunk(const Epilogue& e, const uint32_t
 struct GemmParams {
   int64_t M;
   int N, K;
+  int fp16;
   Epilogue ep;
 };
 
@@ -216,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -253,7 +284,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else if (warp == 1) {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+      const uint32_t idesc = make_idesc(BM, BN, p.fp16);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -287,9 +318,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
     }
   } else {
-    // =========================================================== epilogue warps 2..5 (TMEM lane quarter = warp % 4)
-    const int quarter = warp & 3;
+    // =========================================================== epilogue warps 2..9 (TMEM lane quarter = warp % 4, column half = (warp-2)/4)
+    const int quarter = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter = warp % 4; column half
     const Epilogue& e = p.ep;
+    float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 2) * EPI_STAGE_FLOATS;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       int m_blk, n_blk;
@@ -298,21 +330,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int64_t m = (int64_t)m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      int64_t orow = m;
-      if (e.rpb_in > 0) orow = (m / e.rpb_in) * e.rpb_out + e.row_off + (m % e.rpb_in);
-      const float* gate_row = (e.mode == EPI_RESID && e.gate) ? e.gate + (m % e.gate_period) * e.gate_ld : nullptr;
-      const float* add_row = (e.mode == EPI_STORE && e.addtab) ? e.addtab + (m % e.add_period) * e.add_ld : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N) break;                                    // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tmem_ld_wait();
-        if (row_ok) epilogue_chunk(e, r, n0, p.N, orow, gate_row, add_row);
-      }
+      epilogue_block(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
+                     (int64_t)m_blk * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -340,7 +359,7 @@ template <int NSPLIT> struct Cfg2 {
   static constexpr int HALF_B_BYTES = (BN / 2) * BK * 2;                                 // 16 KiB
   static constexpr int STAGE_BYTES = PLANES * (A_TILE_BYTES + HALF_B_BYTES);             // 32 KiB / 64 KiB per CTA
   static constexpr int STAGES = NSPLIT == 3 ? 3 : 6;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 32 * 32 * 4;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -418,7 +437,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -458,7 +477,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else if (warp == 1) {
     // =========================================================== MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN);
+      const uint32_t idesc = make_idesc(2 * BM, BN, p.fp16);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
@@ -492,9 +511,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       }
     }
   } else {
-    // =========================================================== epilogue warps 2..5 of both CTAs
-    const int quarter = warp & 3;
+    // =========================================================== epilogue warps 2..9 of both CTAs
+    const int quarter = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter = warp % 4; column half
     const Epilogue& e = p.ep;
+    float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 2) * EPI_STAGE_FLOATS;
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       int pm, n_blk;
@@ -503,21 +523,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int64_t m = (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      int64_t orow = m;
-      if (e.rpb_in > 0) orow = (m / e.rpb_in) * e.rpb_out + e.row_off + (m % e.rpb_in);
-      const float* gate_row = (e.mode == EPI_RESID && e.gate) ? e.gate + (m % e.gate_period) * e.gate_ld : nullptr;
-      const float* add_row = (e.mode == EPI_STORE && e.addtab) ? e.addtab + (m % e.add_period) * e.add_ld : nullptr;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        if (n0 >= p.N) break;
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
-        tmem_ld_wait();
-        if (row_ok) epilogue_chunk(e, r, n0, p.N, orow, gate_row, add_row);
-      }
+      epilogue_block(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
+                     (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's barrier counts all 8 epilogue warps
@@ -541,12 +548,12 @@ EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 0;
 int g_gemm_ctas = 2;      // 2: cta_group::2 pair kernel (default); 1: single-CTA kernel (SELFTOK_GEMM_CTAS=1)
 
-int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, int box_rows) {
+int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, int box_rows, int fp16) {
   cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box, estr,
+  CUresult r = g_encode(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -581,25 +588,27 @@ int gemm_tc_init() {
 
 int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* W_hi,
                    const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
-                   cudaStream_t s) {
+                   cudaStream_t s, int fp16) {
   STK_CHECK(g_encode, -3, "gemm_tc_init has not been called");
   STK_CHECK(A_hi && W_hi && M > 0 && N > 0 && K > 0, -1, "gemm_tc: bad arguments");
   STK_CHECK(nsplit == 1 || (nsplit == 3 && A_lo && W_lo), -1, "gemm_tc: nsplit must be 1, or 3 with lo planes");
+  STK_CHECK(!fp16 || nsplit == 1, -1, "gemm_tc: the fp16 mode is single-pass");
+  STK_CHECK(ep.mode != EPI_STORE || ep.addtab == nullptr || ep.add_ld % 4 == 0, -2, "gemm_tc: addtab pitch must be a multiple of 4");
   STK_CHECK(K % 8 == 0, -2, "gemm_tc: K must be a multiple of 8 (16-byte TMA row pitch)");
   STK_CHECK(ep.ldo % 4 == 0 && N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");
   STK_CHECK(ep.mode != EPI_RESID || ep.gate == nullptr || ep.gate_ld % 4 == 0, -2, "gemm_tc: gate pitch must be a multiple of 4");
   CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
   const bool pair = g_gemm_ctas == 2 && g_num_sms >= 2;
   const int b_box = pair ? BN / 2 : BN;
-  STK_TRY(make_map(&ma_hi, A_hi, M, K, BM));
-  STK_TRY(make_map(&mb_hi, W_hi, N, K, b_box));
+  STK_TRY(make_map(&ma_hi, A_hi, M, K, BM, fp16));
+  STK_TRY(make_map(&mb_hi, W_hi, N, K, b_box, fp16));
   if (nsplit == 3) {
-    STK_TRY(make_map(&ma_lo, A_lo, M, K, BM));
-    STK_TRY(make_map(&mb_lo, W_lo, N, K, b_box));
+    STK_TRY(make_map(&ma_lo, A_lo, M, K, BM, fp16));
+    STK_TRY(make_map(&mb_lo, W_lo, N, K, b_box, fp16));
   } else {
     ma_lo = ma_hi; mb_lo = mb_hi;
   }
-  GemmParams p{M, N, K, ep};
+  GemmParams p{M, N, K, fp16, ep};
   const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
   if (pair) {
     const int pairs = (int)((M + 2 * BM - 1) / (2 * BM)) * n_tiles;

@@ -28,6 +28,7 @@ struct Epilogue {
   __nv_bfloat16* out_hi = nullptr;       // EPI_SPLIT
   __nv_bfloat16* out_lo = nullptr;       // may be NULL (single-pass bf16)
   int rpb_in = 0, rpb_out = 0, row_off = 0;
+  int fp16 = 0;                          // EPI_SPLIT: planes hold IEEE half (single-pass fp16 mode) instead of bf16
 };
 
 // ---- fp32 FFMA kernels (kernels_simt.cu) ---------------------------------------------------------------------
@@ -36,7 +37,7 @@ int launch_linear_f32(const float* A, int64_t lda, const float* W, int64_t ldw, 
 // LN (no affine, eps) + modulate; writes fp32 and/or bf16 planes.  shift/scale NULL -> plain LN.
 int launch_ln_mod(const float* x, int64_t ldx, const float* shift, const float* scale, int64_t ld_mod, int period,
                   float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t ldo, int64_t M, int D,
-                  float eps, cudaStream_t s);
+                  float eps, cudaStream_t s, int fp16 = 0);
 // Attention output routing: query rows [0,split) of every image go to the compact buffer A ([B*split, ld]),
 // rows [split,Sq) to buffer B ([B*(Sq-split), ld]).  split == Sq -> everything in A.  Each buffer is fp32 and/or
 // bf16 hi(/lo) planes (NULL pointers are skipped).
@@ -45,6 +46,7 @@ struct AttnOut {
   float* f32_b = nullptr; __nv_bfloat16* hi_b = nullptr; __nv_bfloat16* lo_b = nullptr;
   int split = 0;
   int64_t ld = 0;
+  int fp16 = 0;                          // planes hold IEEE half instead of bf16
 };
 // softmax(q k^T / sqrt(hd)) v in fp32.  q rows: q + b*q_bs + s*q_ld + h*hd; keys = segment 1 (S1 rows) followed by
 // segment 2 (S2 rows).  Rows < ctx_rows only see keys < ctx_keys (renderer rule); ctx_rows = 0 -> dense.
@@ -64,7 +66,7 @@ int launch_patchify(const float* x, float* out, int B, int C, int Hh, int Ww, in
 int launch_unpatchify_axpy(const float* o, const float* x_in, float* x_out, float dt, int B, int C, int g, int p,
                            cudaStream_t s);
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);
-int launch_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t s);
+int launch_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t s, int fp16 = 0);
 // out[b, r, :] = src[r, :] for b in 0..B-1 (broadcast rows), optionally + add[r,:]
 int launch_bcast_rows(const float* src, const float* add, float* out, int B, int64_t rows, int64_t cols, cudaStream_t s);
 // centre crop of a [max,max,D] positional grid to [g,g,D]
@@ -73,15 +75,16 @@ int launch_copy_rows(const float* src, int64_t src_bs, float* dst, int64_t dst_b
 
 // ---- tcgen05 GEMM (gemm_tc.cu) --------------------------------------------------------------------------------
 // A planes [M,K] bf16 row-major (lo NULL iff nsplit == 1), W planes [N,K] bf16 row-major.
+// fp16 != 0: operands are IEEE half planes (nsplit must be 1).
 int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* W_hi,
                    const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
-                   cudaStream_t s);
+                   cudaStream_t s, int fp16 = 0);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes; idempotent
 void gemm_tc_set_ctas(int n);   // 2 (default): cta_group::2 pair kernel; 1: single-CTA kernel
 
 // ---- tensor-core attention (attn_tc.cu) ------------------------------------------------------------------------
 // qkv: packed fp32 [B,S,3,H,64]
 int launch_attention_tc(const float* qkv, int B, int S, int H, int nsplit, int ctx_rows, int ctx_keys,
-                        const AttnOut& out, cudaStream_t s);
+                        const AttnOut& out, cudaStream_t s, int fp16 = 0);
 
 }  // namespace stk

@@ -127,10 +127,10 @@ __global__ void __launch_bounds__(256) linear_f32_kernel(const LinParams p) {
           float g = e.gate ? e.gate[(m % e.gate_period) * e.gate_ld + nn] : 1.0f;
           e.out[orow * e.ldo + nn] = e.resid[orow * e.ldo + nn] + g * y;
         } else {
-          __nv_bfloat16 hi, lo;
-          split_bf16(y, hi, lo);
-          e.out_hi[orow * e.ldo + nn] = hi;
-          if (e.out_lo) e.out_lo[orow * e.ldo + nn] = lo;
+          uint16_t hi, lo;
+          split16(y, e.fp16, hi, lo);
+          reinterpret_cast<uint16_t*>(e.out_hi)[orow * e.ldo + nn] = hi;
+          if (e.out_lo) reinterpret_cast<uint16_t*>(e.out_lo)[orow * e.ldo + nn] = lo;
         }
       }
     }
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
                                                      const float* __restrict__ shift, const float* __restrict__ scale,
                                                      int64_t ld_mod, int period, float* __restrict__ out_f32,
                                                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                                     int64_t ldo, int64_t M, int D, float eps) {
+                                                     int64_t ldo, int64_t M, int D, float eps, int fp16) {
   const int lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
       }
       if (out_f32) reinterpret_cast<float4*>(out_f32 + m * ldo)[idx] = y;
       if (out_hi) {
-        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bf16(y.x, h0, l0); split_bf16(y.y, h1, l1); split_bf16(y.z, h2, l2); split_bf16(y.w, h3, l3);
-        reinterpret_cast<uint2*>(out_hi + m * ldo)[idx] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-        if (out_lo) reinterpret_cast<uint2*>(out_lo + m * ldo)[idx] = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+        uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split16(y.x, fp16, h0, l0); split16(y.y, fp16, h1, l1); split16(y.z, fp16, h2, l2); split16(y.w, fp16, h3, l3);
+        reinterpret_cast<uint2*>(out_hi + m * ldo)[idx] = make_uint2(h0 | ((uint32_t)h1 << 16), h2 | ((uint32_t)h3 << 16));
+        if (out_lo) reinterpret_cast<uint2*>(out_lo + m * ldo)[idx] = make_uint2(l0 | ((uint32_t)l1 << 16), l2 | ((uint32_t)l3 << 16));
       }
     }
   }
@@ -218,16 +218,16 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
 
 int launch_ln_mod(const float* x, int64_t ldx, const float* shift, const float* scale, int64_t ld_mod, int period,
                   float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t ldo, int64_t M, int D,
-                  float eps, cudaStream_t s) {
+                  float eps, cudaStream_t s, int fp16) {
   STK_CHECK(x && M > 0 && D > 0 && D % 4 == 0 && ldx % 4 == 0 && ldo % 4 == 0 && ld_mod % 4 == 0, -1, "ln_mod: bad arguments");
   STK_CHECK((shift == nullptr) == (scale == nullptr), -1, "ln_mod: shift and scale must both be given or both NULL");
   STK_CHECK(D <= 2048, -2, "ln_mod: D > 2048 unsupported");
   const int wpb = 8;
   dim3 grid((unsigned)((M + wpb - 1) / wpb));
   if (D <= 512)
-    ln_mod_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps);
+    ln_mod_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps, fp16);
   else
-    ln_mod_kernel<16><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps);
+    ln_mod_kernel<16><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps, fp16);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;
@@ -378,10 +378,10 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnParams p) 
       const int64_t idx = orow * t.ld + h * HD + tx * DV + d;
       if (of) of[idx] = y;
       if (oh) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(y, hi, lo);
-        oh[idx] = hi;
-        if (ol) ol[idx] = lo;
+        uint16_t hi, lo;
+        split16(y, t.fp16, hi, lo);
+        reinterpret_cast<uint16_t*>(oh)[idx] = hi;
+        if (ol) reinterpret_cast<uint16_t*>(ol)[idx] = lo;
       }
     }
   }
@@ -667,18 +667,18 @@ int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream
   return 0;
 }
 
-__global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n) {
+__global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int64_t n, int fp16) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    __nv_bfloat16 h, l;
-    split_bf16(in[i], h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    uint16_t h, l;
+    split16(in[i], fp16, h, l);
+    reinterpret_cast<uint16_t*>(hi)[i] = h;
+    if (lo) reinterpret_cast<uint16_t*>(lo)[i] = l;
   }
 }
-int launch_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t s) {
+int launch_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t s, int fp16) {
   STK_CHECK(in && hi && n > 0, -1, "split_bf16: bad arguments");
   int64_t blocks = (n + 255) / 256;
-  split_bf16_kernel<<<(unsigned)(blocks > 16384 ? 16384 : blocks), 256, 0, s>>>(in, hi, lo, n);
+  split_bf16_kernel<<<(unsigned)(blocks > 16384 ? 16384 : blocks), 256, 0, s>>>(in, hi, lo, n, fp16);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

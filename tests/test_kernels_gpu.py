@@ -61,7 +61,7 @@ def test_attention_f32(dev, B, Sq, S1, S2, H, hd):
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 192), (1000, 576, 192), (4096, 1536, 1536), (48, 192, 768),
                                     (333, 4608, 1536), (2048, 6144, 1536), (1024, 1536, 6144), (129, 260, 128), (257, 256, 64), (1280, 4608, 1536)])
-@pytest.mark.parametrize("nsplit", [3, 1])
+@pytest.mark.parametrize("nsplit", [3, 1, 0])
 @pytest.mark.parametrize("ctas", [2, 1])
 def test_gemm_tcgen05(dev, M, N, K, nsplit, ctas):
     """tcgen05 GEMM (TMA + TMEM) vs fp64, both the cta_group::2 SM-pair kernel and the single-CTA kernel.
@@ -73,7 +73,7 @@ def test_gemm_tcgen05(dev, M, N, K, nsplit, ctas):
     torch.cuda.synchronize()
     ref = A.double() @ W.double().t() + b.double()
     err = (y.double() - ref).abs().max().item()
-    tol = 2.5e-4 if nsplit == 3 else 6e-2       # bf16x3: ~2^-16 per product, random-walk over K; bf16: 2^-9
+    tol = {3: 2.5e-4, 1: 6e-2, 0: 8e-3}[nsplit]   # bf16x3: ~2^-16 per product, random walk over K; bf16: 2^-9; fp16 (nsplit 0): 2^-12
     assert err < tol, (err, M, N, K, nsplit)
     # and the split really buys precision
     if nsplit == 3 and K >= 192:
@@ -84,7 +84,7 @@ def test_gemm_tcgen05(dev, M, N, K, nsplit, ctas):
 
 @pytest.mark.parametrize("B,S,H,ctx_rows,ctx_keys", [(2, 768, 3, 0, 0), (2, 276, 24, 0, 0), (3, 48, 3, 0, 0), (2, 300, 2, 44, 44),
                                                     (1, 768, 4, 512, 512), (2, 65, 1, 0, 0)])
-@pytest.mark.parametrize("nsplit", [3, 1])
+@pytest.mark.parametrize("nsplit", [3, 1, 0])
 def test_attention_tensor_core(dev, B, S, H, ctx_rows, ctx_keys, nsplit):
     from selftoktokenizer_b200 import capi
     qkv = _rand((B, S, 3, H, 64), 15, dev)
@@ -96,4 +96,4 @@ def test_attention_tensor_core(dev, B, S, H, ctx_rows, ctx_keys, nsplit):
         mask[:ctx_rows, ctx_keys:] = False
     ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, S, H * 64)
     err = (o.double() - ref).abs().max().item()
-    assert err < (3e-5 if nsplit == 3 else 2e-2), err
+    assert err < {3: 3e-5, 1: 2e-2, 0: 3e-3}[nsplit], err

@@ -16,7 +16,7 @@ from selftoktokenizer_b200 import config as C, schedule as S, synth
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-TOL = {"fp32": 2e-4, "bf16x3": 1e-3, "bf16": 0.35}      # max-abs on latents / velocities of O(3) magnitude
+TOL = {"fp32": 2e-4, "bf16x3": 1e-3, "fp16": 1e-3, "bf16": 0.35}      # max-abs on latents / velocities of O(3) magnitude
 
 
 @pytest.fixture(scope="module")
@@ -24,7 +24,7 @@ def tiny_sd():
     return synth.synth_state_dict(C.TINY)
 
 
-@pytest.fixture(scope="module", params=["fp32", "bf16x3", "bf16"])
+@pytest.fixture(scope="module", params=["fp32", "bf16x3", "fp16", "bf16"])
 def tiny_engine(request, tiny_sd):
     from selftoktokenizer_b200.capi import Engine
     eng = Engine(C.TINY, tiny_sd, device=DEV, precision=request.param)
@@ -90,7 +90,7 @@ def test_tiny_shard_invariance(tiny_engine, gold):
     assert torch.equal(full, parts)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "fp16"])
 def test_tiny_renderer(precision, gold):
     from selftoktokenizer_b200.capi import Engine
     g = gold("tiny_renderer")
@@ -130,10 +130,11 @@ def full_sd():
     return synth.synth_state_dict(C.FULL, device=DEV)
 
 
-@pytest.fixture(scope="module")
-def full_engine(full_sd):
+@pytest.fixture(scope="module", params=["bf16x3", "fp16"])
+def full_engine(request, full_sd):
+    """Both parity modes of the decoder: split-bf16 (3 MMAs / product) and single-pass IEEE-half operands."""
     from selftoktokenizer_b200.capi import Engine
-    eng = Engine(C.FULL, full_sd, device=DEV, precision="bf16x3")
+    eng = Engine(C.FULL, full_sd, device=DEV, precision=request.param)
     yield eng
     eng.close()
 
@@ -156,7 +157,7 @@ def test_full_velocity(full_engine, gold):
     for st in (0, 30, 49):
         v = full_engine.dit_velocity(tok, x, st).cpu().numpy()
         err = np.abs(v - g[f"v{st}"]).max()
-        print(f"[bf16x3] full-geometry velocity step {st}: max-abs err {err:.3e} (|v|max {np.abs(g[f'v{st}']).max():.2f})")
+        print(f"[{full_engine.precision}] full-geometry velocity step {st}: max-abs err {err:.3e} (|v|max {np.abs(g[f'v{st}']).max():.2f})")
         assert err < 1e-3
 
 
@@ -167,7 +168,7 @@ def test_full_decode_50_steps(full_engine, gold):
     x = full_engine.decode(tok, torch.from_numpy(g["noise"])).cpu().numpy()
     err = np.abs(x - g["pred_x0"]).max()
     mse = float(((x - g["pred_x0"]) ** 2).mean())
-    print(f"[bf16x3] full-geometry 50-step decode: max-abs err {err:.3e}, mse {mse:.3e}")
+    print(f"[{full_engine.precision}] full-geometry 50-step decode: max-abs err {err:.3e}, mse {mse:.3e}")
     assert err < 1e-3
 
 
