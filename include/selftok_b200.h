@@ -167,7 +167,8 @@ int selftok_k_attention_f32(const float* q_dev, int64_t q_ld, const float* k1_de
                             float* out_dev, int64_t out_ld, int B, int Sq, int H, int hd, void* stream);
 /* Tensor-core (bf16x3 / bf16) attention over a packed qkv buffer [B,S,3,H,64]; ctx_rows = number of leading rows
  * whose queries may only see the first `ctx_keys` keys (renderer rule; pass 0 for plain dense attention).
- * nsplit 3: bf16 hi+lo split, 1: bf16, 0: IEEE half single pass. */
+ * nsplit 3: bf16 hi+lo split, 1: bf16, 0: IEEE half single pass (mma.sync kernel); 10 / 11: the tcgen05 + TMEM kernel
+ * with IEEE half / bf16 operands. */
 int selftok_k_attention_tc(const float* qkv_dev, float* out_dev, int B, int S, int H, int nsplit,
                            int ctx_rows, int ctx_keys, void* stream);
 

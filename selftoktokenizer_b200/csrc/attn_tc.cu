@@ -45,7 +45,8 @@ __device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t&
 }
 
 struct AttnTcParams {
-  const float* qkv;      // [B, S, 3, H, 64]
+  const uint16_t* qkv_hi;   // [B, S, 3, H, 64] 16-bit planes written by the QKV GEMM epilogue (bf16 hi / IEEE half)
+  const uint16_t* qkv_lo;   // bf16 lo plane (NSPLIT == 3) or NULL
   AttnOut out;
   int S, H, ctx_rows, ctx_keys;
   float scale_log2e;
@@ -59,22 +60,26 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S;
   const int64_t row_stride = (int64_t)3 * p.H * HD;
-  const float* base = p.qkv + (int64_t)b * S * row_stride + (int64_t)h * HD;
+  const int64_t base_off = (int64_t)b * S * row_stride + (int64_t)h * HD;
+  const uint16_t* base_hi = p.qkv_hi + base_off;
+  const uint16_t* base_lo = NSPLIT == 3 ? p.qkv_lo + base_off : nullptr;
   // ---- Q fragments (rows r0 = q0 + warp*16 + g, r1 = r0 + 8), kept for the whole kernel
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
   uint32_t qh[4][4], ql[4][4];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
     const int d0 = kk * 16 + tig * 2;
-    float2 z = make_float2(0.f, 0.f);
-    float2 x00 = r0 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r0 * row_stride + d0) : z;
-    float2 x10 = r1 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r1 * row_stride + d0) : z;
-    float2 x01 = r0 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r0 * row_stride + d0 + 8) : z;
-    float2 x11 = r1 < S ? *reinterpret_cast<const float2*>(base + (int64_t)r1 * row_stride + d0 + 8) : z;
-    split2<FP16>(x00.x, x00.y, qh[kk][0], ql[kk][0]);
-    split2<FP16>(x10.x, x10.y, qh[kk][1], ql[kk][1]);
-    split2<FP16>(x01.x, x01.y, qh[kk][2], ql[kk][2]);
-    split2<FP16>(x11.x, x11.y, qh[kk][3], ql[kk][3]);
+    const int64_t o0 = (int64_t)r0 * row_stride + d0, o1 = (int64_t)r1 * row_stride + d0;
+    qh[kk][0] = r0 < S ? *reinterpret_cast<const uint32_t*>(base_hi + o0) : 0u;
+    qh[kk][1] = r1 < S ? *reinterpret_cast<const uint32_t*>(base_hi + o1) : 0u;
+    qh[kk][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(base_hi + o0 + 8) : 0u;
+    qh[kk][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(base_hi + o1 + 8) : 0u;
+    if (NSPLIT == 3) {
+      ql[kk][0] = r0 < S ? *reinterpret_cast<const uint32_t*>(base_lo + o0) : 0u;
+      ql[kk][1] = r1 < S ? *reinterpret_cast<const uint32_t*>(base_lo + o1) : 0u;
+      ql[kk][2] = r0 < S ? *reinterpret_cast<const uint32_t*>(base_lo + o0 + 8) : 0u;
+      ql[kk][3] = r1 < S ? *reinterpret_cast<const uint32_t*>(base_lo + o1 + 8) : 0u;
+    }
   }
   float o[8][4];
 #pragma unroll
@@ -86,24 +91,25 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
 
   for (int k0 = 0; k0 < kmax_cta; k0 += BKV) {
     __syncthreads();
-    // ---- stage K (row-major) and V (transposed) tiles as bf16 hi/lo planes
-    for (int f = tid; f < BKV * HD / 4; f += 128) {
-      const int key = f >> 4, d4 = (f & 15) * 4;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    // ---- stage the K and V tiles (already 16-bit in HBM): 64 keys x 128 B per plane, 16 B per thread-copy
+    for (int f = tid; f < BKV * 8; f += 128) {
+      const int key = f >> 3, ch = (f & 7) * 8;
+      uint4 kh = make_uint4(0, 0, 0, 0), vh = kh, kl = kh, vl = kh;
       if (k0 + key < S) {
-        const float* rp = base + (int64_t)(k0 + key) * row_stride + d4;
-        kv = *reinterpret_cast<const float4*>(rp + (int64_t)p.H * HD);
-        vv = *reinterpret_cast<const float4*>(rp + (int64_t)2 * p.H * HD);
+        const int64_t ro = (int64_t)(k0 + key) * row_stride + ch;
+        kh = *reinterpret_cast<const uint4*>(base_hi + ro + (int64_t)p.H * HD);
+        vh = *reinterpret_cast<const uint4*>(base_hi + ro + (int64_t)2 * p.H * HD);
+        if (NSPLIT == 3) {
+          kl = *reinterpret_cast<const uint4*>(base_lo + ro + (int64_t)p.H * HD);
+          vl = *reinterpret_cast<const uint4*>(base_lo + ro + (int64_t)2 * p.H * HD);
+        }
       }
-      uint32_t h01, l01, h23, l23;
-      split2<FP16>(kv.x, kv.y, h01, l01);
-      split2<FP16>(kv.z, kv.w, h23, l23);
-      *reinterpret_cast<uint2*>(&Ks[0][key][d4]) = make_uint2(h01, h23);
-      if (NSPLIT == 3) *reinterpret_cast<uint2*>(&Ks[1][key][d4]) = make_uint2(l01, l23);
-      split2<FP16>(vv.x, vv.y, h01, l01);
-      split2<FP16>(vv.z, vv.w, h23, l23);
-      *reinterpret_cast<uint2*>(&Vs[0][key][d4]) = make_uint2(h01, h23);
-      if (NSPLIT == 3) *reinterpret_cast<uint2*>(&Vs[1][key][d4]) = make_uint2(l01, l23);
+      *reinterpret_cast<uint4*>(&Ks[0][key][ch]) = kh;
+      *reinterpret_cast<uint4*>(&Vs[0][key][ch]) = vh;
+      if (NSPLIT == 3) {
+        *reinterpret_cast<uint4*>(&Ks[1][key][ch]) = kl;
+        *reinterpret_cast<uint4*>(&Vs[1][key][ch]) = vl;
+      }
     }
     __syncthreads();
     // ---- S = Q K^T  (16 x 64 per warp)
@@ -221,12 +227,14 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const AttnTcParams p)
 
 }  // namespace
 
-int launch_attention_tc(const float* qkv, int B, int S, int H, int nsplit, int ctx_rows, int ctx_keys,
-                        const AttnOut& out, cudaStream_t s, int fp16) {
-  STK_CHECK(qkv && B > 0 && S > 0 && H > 0, -1, "attention_tc: bad arguments");
+int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int B, int S, int H, int nsplit,
+                        int ctx_rows, int ctx_keys, const AttnOut& out, cudaStream_t s, int fp16) {
+  STK_CHECK(qkv_hi && B > 0 && S > 0 && H > 0, -1, "attention_tc: bad arguments");
+  STK_CHECK(nsplit != 3 || qkv_lo, -1, "attention_tc: the split mode needs the lo plane");
   STK_CHECK(nsplit == 1 || nsplit == 3, -1, "attention_tc: nsplit must be 1 or 3");
   STK_CHECK(out.ld % 2 == 0, -1, "attention_tc: output pitch must be even");
-  AttnTcParams p{qkv, out, S, H, ctx_rows, ctx_keys, 0.125f * 1.4426950408889634f};
+  AttnTcParams p{reinterpret_cast<const uint16_t*>(qkv_hi), reinterpret_cast<const uint16_t*>(qkv_lo), out, S, H, ctx_rows, ctx_keys,
+                 0.125f * 1.4426950408889634f};
   dim3 grid((S + BQ - 1) / BQ, H, B);
   STK_CHECK(!fp16 || nsplit == 1, -1, "attention_tc: the fp16 mode is single-pass");
   if (nsplit == 3) attention_tc_kernel<3, 0><<<grid, 128, 0, s>>>(p);

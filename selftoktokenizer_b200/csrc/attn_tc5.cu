@@ -1,0 +1,351 @@
+// Joint attention of the MMDiT on tcgen05 tensor cores with TMEM accumulators (sm_100a), head_dim 64, single-pass
+// 16-bit operands (IEEE half or bf16), fp32 softmax.
+//
+//   CTA            128 query rows of one (image, head); grid (ceil(S/128), H, B); 3 CTAs co-reside per SM (64 KiB smem,
+//                  128 TMEM columns each) so one CTA's softmax overlaps another CTA's MMAs
+//   warp 0         TMA producer: Q tile once, then K and V tiles (64 keys x 64 dims) through a 2-stage ring
+//   warp 1         MMA issuer (one thread):  S = Q K^T  -> TMEM cols [0,64)   (UMMA 128x64x16 x4, both operands K-major)
+//                                            O += P V   -> TMEM cols [64,128) (UMMA 128x64x16 x4, A = P K-major from smem,
+//                                                                              B = V MN-major straight from the TMA tile)
+//   warps 2-5      one thread per query row (TMEM lane): tcgen05.ld the row of S, online softmax in registers (no
+//                  shuffles), rescale its row of O in TMEM (tcgen05.ld / tcgen05.st), write P as 16-bit into the
+//                  SWIZZLE_128B A-operand tile, finally normalise O and store it as the A-operand planes of the proj GEMM
+//
+// Same contract as attn_tc.cu (sd3/mmdit.py:521-531, sd3/other_impls.py:37-45): dense non-causal attention over the joint
+// [context prefix ; image] sequence; rows < ctx_rows only see keys < ctx_keys (renderer rule, mmdit.py:1581).
+#include "common.cuh"
+#include "kernels.h"
+
+#include <cuda.h>
+
+namespace stk {
+
+// provided by gemm_tc.cu
+int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                       int fp16);
+
+namespace {
+
+constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 2;
+constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2, P_BYTES = BQ * BKV * 2;
+constexpr int SMEM_TILES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES;      // 16 + 32 + 16 = 64 KiB
+constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 128;
+constexpr int TMEM_COLS = 128;
+constexpr int NUM_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3ff) == 0 && clock64() - t0 > 8000000000LL) {
+      printf("selftok attn_tc5: mbarrier timeout (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// SWIZZLE_128B shared-memory descriptors (cute::UMMA::SmemDescriptor): 8 rows x 128 B atoms, SBO = 1024 B between atoms.
+// The same encoding serves the K-major operands (Q, K, P: 64 K-elements per 128 B row) and the MN-major V tile (64 head
+// dims contiguous per key row, 8 keys per atom); the major-ness is selected in the instruction descriptor.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B format (0 = F16, 1 = BF16), a_major bit 15, b_major bit 16 (1 = MN-major)
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, int fp16, int b_mn_major) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct Attn5Params {
+  AttnOut out;
+  int S, H, ctx_rows, ctx_keys, fp16;
+  float scale_log2e;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 3)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_s = base;
+  const uint32_t kv_s = base + Q_BYTES;                       // stage st: K at kv_s + st*2*KV_TILE_BYTES, V right after
+  const uint32_t p_s = kv_s + KV_STAGES * 2 * KV_TILE_BYTES;
+  const uint32_t bars = p_s + P_BYTES;
+  const uint32_t q_full = bars, s_full = bars + 8, p_ready = bars + 16, o_final = bars + 24;
+  auto kv_full = [&](int st) { return bars + 32 + 8u * st; };
+  auto kv_empty = [&](int st) { return bars + 48 + 8u * st; };
+  const uint32_t tmem_slot = bars + 64;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* p_ptr = smem_raw + (p_s - smem_u32(smem_raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int S = p.S;
+  const int kmax_cta = (q0 + BQ <= p.ctx_rows) ? p.ctx_keys : S;          // every row of this CTA is a context row
+  const int n_tiles = (kmax_cta + BKV - 1) / BKV;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_final, 1);
+    for (int st = 0; st < KV_STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64;
+
+  if (warp == 0) {
+    // =========================================================== TMA producer
+    if (lane == 0) {
+      const int row0 = b * S;                                           // first row of this image in the [B*S, 3*H*64] matrix
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_2d(q_s, &map_q, q_full, h * HD, row0 + q0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        mbar_wait(kv_empty(st), ph ^ 1);
+        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
+        mbar_expect_tx(kv_full(st), 2 * KV_TILE_BYTES);
+        tma_load_2d(ks, &map_kv, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
+        tma_load_2d(ks + KV_TILE_BYTES, &map_kv, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+      }
+    }
+  } else if (warp == 1) {
+    // =========================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = make_idesc(BQ, BKV, p.fp16, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
+      const uint32_t idesc_pv = make_idesc(BQ, HD, p.fp16, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES, vs = ks + KV_TILE_BYTES;
+        mbar_wait(kv_full(st), ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)                                // K dimension = head dim: 32 B per k-step inside the row
+          tc_mma_f16(s_tmem, make_smem_desc(q_s + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        tc_commit(s_full);
+        mbar_wait(p_ready, j & 1);                                       // P_j in smem, O rescaled, S consumed
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k)                               // K dimension = keys: 16 keys = 2 atoms of 8 key rows
+          tc_mma_f16(o_tmem, make_smem_desc(p_s + k * 32), make_smem_desc(vs + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(kv_empty(st));                                         // K/V stage reusable once QK_j and PV_j retire
+      }
+      tc_commit(o_final);
+    }
+  } else {
+    // =========================================================== softmax / correction / epilogue: thread = query row
+    const int quarter = warp & 3;
+    const int rl = quarter * 32 + lane;                                  // row inside the tile = TMEM lane
+    const int row = q0 + rl;
+    const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      uint32_t r0[32], r1[32];
+      tmem_ld32(s_tmem + lane_addr, r0);
+      tmem_ld32(s_tmem + lane_addr + 32, r1);
+      tmem_ld_wait();
+      const int k0 = j * BKV;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float a = __uint_as_float(r0[i]) * p.scale_log2e, c = __uint_as_float(r1[i]) * p.scale_log2e;
+        if (k0 + i >= kmax) a = -INFINITY;
+        if (k0 + 32 + i >= kmax) c = -INFINITY;
+        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(c);
+        mx = fmaxf(mx, fmaxf(a, c));
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float sub = (m_new == -INFINITY) ? 0.f : m_new;
+      const float corr = (m_new == -INFINITY) ? 1.f : exp2f(m_run - m_new);
+      float rs = 0.f;
+      // P (16-bit) into the SWIZZLE_128B K-major A-operand tile: row rl at rl*128 B, 16-byte chunk c stored at c ^ (rl & 7)
+      uint8_t* prow = p_ptr + rl * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = c * 8 + q * 2;
+          const float e0 = exp2f(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]) - sub);
+          const float e1 = exp2f(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]) - sub);
+          rs += e0 + e1;
+          uint16_t h0, h1, l0, l1;
+          split16(e0, p.fp16 != 0, h0, l0);
+          split16(e1, p.fp16 != 0, h1, l1);
+          w[q] = h0 | ((uint32_t)h1 << 16);
+        }
+        *reinterpret_cast<uint4*>(prow + ((c ^ (rl & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l_run = l_run * corr + rs;
+      m_run = m_new;
+      if (j > 0) {
+        // rescale this row of O (PV_{j-1} has retired: s_full(j) was committed after it)
+        tmem_ld32(o_tmem + lane_addr, r0);
+        tmem_ld32(o_tmem + lane_addr + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
+          r1[i] = __float_as_uint(__uint_as_float(r1[i]) * corr);
+        }
+        tmem_st32(o_tmem + lane_addr, r0);
+        tmem_st32(o_tmem + lane_addr + 32, r1);
+        tmem_st_wait();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // st.shared of P -> visible to the tensor core
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+    }
+    // ---- epilogue: O / l -> 16-bit planes (A operand of the proj GEMM) and / or fp32
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    uint32_t r0[32], r1[32];
+    tmem_ld32(o_tmem + lane_addr, r0);
+    tmem_ld32(o_tmem + lane_addr + 32, r1);
+    tmem_ld_wait();
+    if (row < S) {
+      const float inv = 1.0f / l_run;
+      const AttnOut& t = p.out;
+      const bool inA = row < t.split;
+      const int64_t orow = inA ? ((int64_t)b * t.split + row) : ((int64_t)b * (S - t.split) + (row - t.split));
+      float* of = inA ? t.f32_a : t.f32_b;
+      uint16_t* oh = reinterpret_cast<uint16_t*>(inA ? t.hi_a : t.hi_b);
+      uint16_t* ol = reinterpret_cast<uint16_t*>(inA ? t.lo_a : t.lo_b);
+      const int64_t o = orow * t.ld + (int64_t)h * HD;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float y[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int i = c * 8 + q;
+          y[q] = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) * inv;
+        }
+        if (of) {
+          *reinterpret_cast<float4*>(of + o + c * 8) = make_float4(y[0], y[1], y[2], y[3]);
+          *reinterpret_cast<float4*>(of + o + c * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+        }
+        if (oh) {
+          uint16_t hh[8], ll[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) split16(y[q], t.fp16 != 0, hh[q], ll[q]);
+          *reinterpret_cast<uint4*>(oh + o + c * 8) = make_uint4(hh[0] | ((uint32_t)hh[1] << 16), hh[2] | ((uint32_t)hh[3] << 16),
+                                                                 hh[4] | ((uint32_t)hh[5] << 16), hh[6] | ((uint32_t)hh[7] << 16));
+          if (ol) *reinterpret_cast<uint4*>(ol + o + c * 8) = make_uint4(ll[0] | ((uint32_t)ll[1] << 16), ll[2] | ((uint32_t)ll[3] << 16),
+                                                                         ll[4] | ((uint32_t)ll[5] << 16), ll[6] | ((uint32_t)ll[7] << 16));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+  }
+}
+
+bool g_attr_set = false;
+
+}  // namespace
+
+int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
+                         cudaStream_t s, int fp16) {
+  STK_CHECK(qkv16 && B > 0 && S > 0 && H > 0, -1, "attention_tc5: bad arguments");
+  STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
+  STK_TRY(gemm_tc_init());
+  if (!g_attr_set) {
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    g_attr_set = true;
+  }
+  CUtensorMap mq, mkv;
+  const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)3 * H * HD;
+  STK_TRY(make_tensor_map_2d(&mq, qkv16, rows, cols, BQ, HD, fp16));
+  STK_TRY(make_tensor_map_2d(&mkv, qkv16, rows, cols, BKV, HD, fp16));
+  Attn5Params p{out, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
+  dim3 grid((S + BQ - 1) / BQ, H, B);
+  attention_tc5_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  count_launch();
+  STK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace stk

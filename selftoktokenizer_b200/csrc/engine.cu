@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -36,7 +37,8 @@ struct DecodeWs {       // activation workspace of the MMDiT for one batch size
   int B = 0;
   int64_t* tokens = nullptr;
   float *outs_q = nullptr, *x_lat = nullptr, *patch = nullptr, *ctx0 = nullptr, *ctx = nullptr, *x = nullptr;
-  float *qkv = nullptr, *o_final = nullptr;
+  float *qkv = nullptr, *o_final = nullptr;      // qkv: fp32 joint buffer (fp32 mode only)
+  bf16 *qkv_hi = nullptr, *qkv_lo = nullptr;     // joint q/k/v as 16-bit planes [B,S,3,H,64] (tensor-core modes)
   // fp32 mode activations
   float *a_c = nullptr, *a_x = nullptr, *attn_c = nullptr, *attn_x = nullptr, *h_c = nullptr, *h_x = nullptr;
   // tensor-core mode activations (bf16 planes)
@@ -58,6 +60,7 @@ struct selftok_engine {
   int D = 0, H = 0, Nimg = 0, Nenc = 0;
   bool finalized = false;
   bool use_graph = true;
+  bool attn_tcgen05 = true;             // single-pass modes: tcgen05/TMEM attention (SELFTOK_ATTN=mma selects the mma.sync kernel)
   std::unordered_map<std::string, Tensor> w;
   std::unordered_map<std::string, WPack> wp;
   std::vector<void*> allocs;            // tables + packed weights
@@ -192,6 +195,10 @@ extern "C" __attribute__((visibility("default"))) int selftok_create(const selft
   e->H = cfg->dit_depth;
   e->Nimg = (cfg->latent / cfg->dit_patch) * (cfg->latent / cfg->dit_patch);
   e->Nenc = (cfg->latent / cfg->enc_patch) * (cfg->latent / cfg->enc_patch);
+  {
+    const char* v = getenv("SELFTOK_ATTN");
+    if (v && std::string(v) == "mma") e->attn_tcgen05 = false;
+  }
   if (tc_mode(e)) {
     int st = gemm_tc_init();
     if (st != 0) { delete e; return st; }
@@ -526,10 +533,10 @@ static int ensure_dws(selftok_engine* e, int B) {
   STK_TRY(dalloc(e, P, &w.ctx0, B * K * D));
   STK_TRY(dalloc(e, P, &w.ctx, B * K * D));
   STK_TRY(dalloc(e, P, &w.x, B * N * D));
-  STK_TRY(dalloc(e, P, &w.qkv, B * S * 3 * D));
   STK_TRY(dalloc(e, P, &w.o_final, B * N * c.dit_patch * c.dit_patch * c.in_channels));
   STK_TRY(dalloc(e, P, &w.a_x, B * N * D));                       // fp32 LN output of the final layer (both modes)
   if (!tc_mode(e)) {
+    STK_TRY(dalloc(e, P, &w.qkv, B * S * 3 * D));
     STK_TRY(dalloc(e, P, &w.a_c, B * K * D));
     STK_TRY(dalloc(e, P, &w.attn_c, B * K * D));
     STK_TRY(dalloc(e, P, &w.attn_x, B * N * D));
@@ -537,6 +544,8 @@ static int ensure_dws(selftok_engine* e, int B) {
     STK_TRY(dalloc(e, P, &w.h_x, B * N * 4 * D));
   } else {
     const bool lo = nsplit(e) == 3;
+    STK_TRY(dalloc(e, P, &w.qkv_hi, B * S * 3 * D));
+    if (lo) STK_TRY(dalloc(e, P, &w.qkv_lo, B * S * 3 * D));
     STK_TRY(dalloc(e, P, &w.a_c_hi, B * K * D));
     STK_TRY(dalloc(e, P, &w.a_x_hi, B * N * D));
     STK_TRY(dalloc(e, P, &w.attn_c_hi, B * K * D));
@@ -569,6 +578,7 @@ static int pre_attention(selftok_engine* e, const std::string& blk, const float*
     return lin32(e, blk + "attn.qkv", a32, D, M, ep, s);
   }
   PROF(PC_LN, launch_ln_mod(resid, D, shift, scale, ld_mod, period, nullptr, a_hi, a_lo, D, M, D, 1e-6f, s, is_fp16(e)));
+  ep.mode = EPI_SPLIT; ep.out = nullptr; ep.out_hi = w.qkv_hi; ep.out_lo = w.qkv_lo;      // q/k/v leave the GEMM as 16-bit planes
   return lintc(e, blk + "attn.qkv", a_hi, a_lo, M, ep, s);
 }
 
@@ -630,7 +640,10 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
     } else {
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
       ao.fp16 = is_fp16(e);
-      PROF(PC_ATTN, launch_attention_tc(w.qkv, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, is_fp16(e)));
+      if (nsplit(e) == 1 && e->attn_tcgen05)
+        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e)));
+      else
+        PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, is_fp16(e)));
     }
     if (!last)
       STK_TRY(post_attention(e, pc, w.ctx, Mc, cmod, 6 * D, Kc, w.attn_c, w.attn_c_hi, w.attn_c_lo, w.a_c, w.a_c_hi, w.a_c_lo,
@@ -898,10 +911,22 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_f32(co
 
 extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(const float* qkv, float* out, int B, int S, int H, int ns, int ctx_rows, int ctx_keys,
                                       void* stream) {
-  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
-  const int fp16 = ns == 0;
-  if (fp16) ns = 1;
+  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3 || ns == 10 || ns == 11), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
+  const bool tc5 = ns >= 10;                    // 10: tcgen05 kernel, IEEE half; 11: tcgen05 kernel, bf16
+  const int fp16 = ns == 0 || ns == 10;
+  if (ns != 3) ns = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t n = (int64_t)B * S * 3 * H * 64;
+  bf16 *qh, *ql = nullptr;
+  STK_CUDA(cudaMalloc(&qh, sizeof(bf16) * n));
+  if (ns == 3) STK_CUDA(cudaMalloc(&ql, sizeof(bf16) * n));
+  int st = launch_split_bf16(qkv, qh, ql, n, s, fp16);
   AttnOut ao;
   ao.f32_a = out; ao.split = S; ao.ld = (int64_t)H * 64;
-  return launch_attention_tc(qkv, B, S, H, ns, ctx_rows, ctx_keys, ao, (cudaStream_t)stream, fp16);
+  if (!st && tc5) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
+  else if (!st) st = launch_attention_tc(qh, ql, B, S, H, ns, ctx_rows, ctx_keys, ao, s, fp16);
+  cudaStreamSynchronize(s);
+  cudaFree(qh);
+  if (ql) cudaFree(ql);
+  return st;
 }

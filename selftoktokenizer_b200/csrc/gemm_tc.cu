@@ -565,6 +565,24 @@ int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, in
 
 }  // namespace
 
+// Generic 2-D SWIZZLE_128B tensor map over a row-major 16-bit matrix [rows, cols] (box_cols * 2 bytes must be 128).
+int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, uint32_t box_cols,
+                       int fp16) {
+  STK_CHECK(g_encode, -3, "gemm_tc_init has not been called");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return -5;
+  }
+  return 0;
+}
+
 void gemm_tc_set_ctas(int n) { g_gemm_ctas = n == 1 ? 1 : 2; }
 
 int gemm_tc_init() {

@@ -83,8 +83,12 @@ int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes; 
 void gemm_tc_set_ctas(int n);   // 2 (default): cta_group::2 pair kernel; 1: single-CTA kernel
 
 // ---- tensor-core attention (attn_tc.cu) ------------------------------------------------------------------------
-// qkv: packed fp32 [B,S,3,H,64]
-int launch_attention_tc(const float* qkv, int B, int S, int H, int nsplit, int ctx_rows, int ctx_keys,
-                        const AttnOut& out, cudaStream_t s, int fp16 = 0);
+// qkv planes: packed 16-bit [B,S,3,H,64] (hi, and lo for nsplit == 3), written by the QKV GEMM epilogue
+int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int B, int S, int H, int nsplit,
+                        int ctx_rows, int ctx_keys, const AttnOut& out, cudaStream_t s, int fp16 = 0);
+
+// tcgen05 / TMEM attention (attn_tc5.cu), single-pass 16-bit operands (fp16 != 0: IEEE half, else bf16)
+int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
+                         cudaStream_t s, int fp16);
 
 }  // namespace stk
