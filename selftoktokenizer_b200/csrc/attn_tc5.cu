@@ -124,6 +124,19 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n, int fp16, int b_mn_
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two fp32 -> packed 16-bit pair (IEEE half or bf16), one cvt instruction
+__device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
+  uint32_t r;
+  if (fp16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 struct Attn5Params {
   AttnOut out;
   int S, H, ctx_rows, ctx_keys, fp16;
@@ -223,18 +236,20 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       tmem_ld32(s_tmem + lane_addr + 32, r1);
       tmem_ld_wait();
       const int k0 = j * BKV;
+      // row maximum on the raw scores (the scale is positive); masking only on tiles that straddle the row's key limit
       float mx = -INFINITY;
+      if (k0 + BKV > kmax) {                                              // thread-level branch, no collectives inside
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float a = __uint_as_float(r0[i]) * p.scale_log2e, c = __uint_as_float(r1[i]) * p.scale_log2e;
-        if (k0 + i >= kmax) a = -INFINITY;
-        if (k0 + 32 + i >= kmax) c = -INFINITY;
-        r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(c);
-        mx = fmaxf(mx, fmaxf(a, c));
+        for (int i = 0; i < 32; ++i) {
+          if (k0 + i >= kmax) r0[i] = 0xff800000u;                        // -inf
+          if (k0 + 32 + i >= kmax) r1[i] = 0xff800000u;
+        }
       }
-      const float m_new = fmaxf(m_run, mx);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2e);
       const float sub = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = (m_new == -INFINITY) ? 1.f : exp2f(m_run - m_new);
+      const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
       float rs = 0.f;
       // P (16-bit) into the SWIZZLE_128B K-major A-operand tile: row rl at rl*128 B, 16-byte chunk c stored at c ^ (rl & 7)
       uint8_t* prow = p_ptr + rl * 128;
@@ -244,20 +259,17 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int i = c * 8 + q * 2;
-          const float e0 = exp2f(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]) - sub);
-          const float e1 = exp2f(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]) - sub);
+          const float e0 = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), p.scale_log2e, -sub));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), p.scale_log2e, -sub));
           rs += e0 + e1;
-          uint16_t h0, h1, l0, l1;
-          split16(e0, p.fp16 != 0, h0, l0);
-          split16(e1, p.fp16 != 0, h1, l1);
-          w[q] = h0 | ((uint32_t)h1 << 16);
+          w[q] = pack2_16(e0, e1, p.fp16 != 0);
         }
         *reinterpret_cast<uint4*>(prow + ((c ^ (rl & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       l_run = l_run * corr + rs;
       m_run = m_new;
-      if (j > 0) {
-        // rescale this row of O (PV_{j-1} has retired: s_full(j) was committed after it)
+      // rescale O only when some row of this warp moved its maximum (PV_{j-1} has retired: s_full(j) was committed after it)
+      if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
         tmem_ld32(o_tmem + lane_addr, r0);
         tmem_ld32(o_tmem + lane_addr + 32, r1);
         tmem_ld_wait();
