@@ -107,13 +107,18 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class Engine:
     """One handle (`selftok_handle_t`) on one device: weights, static tables, workspaces, CUDA graphs."""
 
-    def __init__(self, dims: SelftokDims, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "fp16",
+    def __init__(self, dims: SelftokDims, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "auto",
                  steps: int = 50, start: float = 1.0):
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise SelftokError("no CUDA device: selftok_b200 has no CPU fallback")
         self.dims = dims
         self.device = torch.device(device)
+        if precision == "auto":
+            # 50-step sampler: single-pass IEEE-half operands (2.9e-4 on the final latents; per-step errors average out).
+            # One-pass renderer: its output IS one network evaluation (fp16 measures 1.05e-3 there), and a single pass
+            # costs 1/50 of a decode, so it runs the fp32-faithful split-bf16 arithmetic (5e-5).
+            precision = "bf16x3" if dims.renderer else "fp16"
         self.precision = precision
         dims.validate()
         cfg = _Config(K=dims.K, latent=dims.latent, in_channels=dims.in_channels, enc_patch=dims.enc_patch,

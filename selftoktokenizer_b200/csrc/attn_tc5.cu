@@ -1,11 +1,11 @@
 // Joint attention of the MMDiT on tcgen05 tensor cores with TMEM accumulators (sm_100a), head_dim 64, single-pass
 // 16-bit operands (IEEE half or bf16), fp32 softmax.
 //
-//   CTA            128 query rows of one (image, head); grid (ceil(S/128), H, B); 3 CTAs co-reside per SM (64 KiB smem,
-//                  128 TMEM columns each) so one CTA's softmax overlaps another CTA's MMAs
-//   warp 0         TMA producer: Q tile once, then K and V tiles (64 keys x 64 dims) through a 2-stage ring
-//   warp 1         MMA issuer (one thread):  S = Q K^T  -> TMEM cols [0,64)   (UMMA 128x64x16 x4, both operands K-major)
-//                                            O += P V   -> TMEM cols [64,128) (UMMA 128x64x16 x4, A = P K-major from smem,
+//   CTA            128 query rows of one (image, head); grid (ceil(S/128), H, B); 2 CTAs co-reside per SM (80 KiB smem,
+//                  256 TMEM columns each); S is double-buffered in TMEM so Q K^T of tile j+1 overlaps the softmax of tile j
+//   warp 0         TMA producer: Q tile once, then K and V tiles (64 keys x 64 dims) through a 3-stage ring
+//   warp 1         MMA issuer (one thread):  S = Q K^T  -> TMEM cols [0,64) / [64,128) (UMMA 128x64x16 x4, both operands K-major)
+//                                            O += P V   -> TMEM cols [128,192)      (UMMA 128x64x16 x4, A = P K-major from smem,
 //                                                                              B = V MN-major straight from the TMA tile)
 //   warps 2-5      one thread per query row (TMEM lane): tcgen05.ld the row of S, online softmax in registers (no
 //                  shuffles), rescale its row of O in TMEM (tcgen05.ld / tcgen05.st), write P as 16-bit into the
@@ -26,11 +26,11 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 namespace {
 
-constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 2;
+constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 3;
 constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2, P_BYTES = BQ * BKV * 2;
-constexpr int SMEM_TILES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES;      // 16 + 32 + 16 = 64 KiB
+constexpr int SMEM_TILES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES;      // 16 + 48 + 16 = 80 KiB
 constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 128;
-constexpr int TMEM_COLS = 128;
+constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O [128,192)
 constexpr int NUM_THREADS = 192;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,7 +143,7 @@ struct Attn5Params {
   float scale_log2e;
 };
 
-__global__ void __launch_bounds__(NUM_THREADS, 3)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -151,10 +151,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t kv_s = base + Q_BYTES;                       // stage st: K at kv_s + st*2*KV_TILE_BYTES, V right after
   const uint32_t p_s = kv_s + KV_STAGES * 2 * KV_TILE_BYTES;
   const uint32_t bars = p_s + P_BYTES;
-  const uint32_t q_full = bars, s_full = bars + 8, p_ready = bars + 16, o_final = bars + 24;
-  auto kv_full = [&](int st) { return bars + 32 + 8u * st; };
-  auto kv_empty = [&](int st) { return bars + 48 + 8u * st; };
-  const uint32_t tmem_slot = bars + 64;
+  const uint32_t q_full = bars, p_ready = bars + 8, pv_done = bars + 16;
+  auto s_full = [&](int sb) { return bars + 24 + 8u * sb; };
+  auto kv_full = [&](int st) { return bars + 40 + 8u * st; };
+  auto kv_empty = [&](int st) { return bars + 64 + 8u * st; };
+  const uint32_t tmem_slot = bars + 96;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* p_ptr = smem_raw + (p_s - smem_u32(smem_raw));
 
@@ -165,7 +166,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int n_tiles = (kmax_cta + BKV - 1) / BKV;
 
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_ready, 4); mbar_init(o_final, 1);
+    mbar_init(q_full, 1); mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(p_ready, 4); mbar_init(pv_done, 1);
     for (int st = 0; st < KV_STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -177,7 +178,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t s_tmem = tmem_base, o_tmem = tmem_base + 64;
+  const uint32_t s_tmem0 = tmem_base, o_tmem = tmem_base + 128;       // S buffer sb at s_tmem0 + 64 * sb
 
   if (warp == 0) {
     // =========================================================== TMA producer
@@ -201,24 +202,29 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const uint32_t idesc_qk = make_idesc(BQ, BKV, p.fp16, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
       const uint32_t idesc_pv = make_idesc(BQ, HD, p.fp16, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
       mbar_wait(q_full, 0);
-      for (int j = 0; j < n_tiles; ++j) {
+      auto issue_qk = [&](int j) {                                       // S[j & 1] = Q K_j^T
         const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES, vs = ks + KV_TILE_BYTES;
-        mbar_wait(kv_full(st), ph);
+        mbar_wait(kv_full(st), (j / KV_STAGES) & 1);
         tc_fence_after();
+        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)                                // K dimension = head dim: 32 B per k-step inside the row
-          tc_mma_f16(s_tmem, make_smem_desc(q_s + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-        tc_commit(s_full);
-        mbar_wait(p_ready, j & 1);                                       // P_j in smem, O rescaled, S consumed
+          tc_mma_f16(s_tmem0 + 64 * (j & 1), make_smem_desc(q_s + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        tc_commit(s_full(j & 1));
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) issue_qk(j + 1);                            // overlaps the softmax of tile j (S is double-buffered)
+        const int st = j % KV_STAGES;
+        const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
+        mbar_wait(p_ready, j & 1);                                       // P_j in smem, O rescaled, S[j & 1] consumed
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)                               // K dimension = keys: 16 keys = 2 atoms of 8 key rows
           tc_mma_f16(o_tmem, make_smem_desc(p_s + k * 32), make_smem_desc(vs + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(kv_empty(st));                                         // K/V stage reusable once QK_j and PV_j retire
+        tc_commit(pv_done);                                              // O and the P tile are free again
       }
-      tc_commit(o_final);
     }
   } else {
     // =========================================================== softmax / correction / epilogue: thread = query row
@@ -229,11 +235,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full(j & 1), (j >> 1) & 1);
       tc_fence_after();
       uint32_t r0[32], r1[32];
-      tmem_ld32(s_tmem + lane_addr, r0);
-      tmem_ld32(s_tmem + lane_addr + 32, r1);
+      tmem_ld32(s_tmem0 + 64 * (j & 1) + lane_addr, r0);
+      tmem_ld32(s_tmem0 + 64 * (j & 1) + lane_addr + 32, r1);
       tmem_ld_wait();
       const int k0 = j * BKV;
       // row maximum on the raw scores (the scale is positive); masking only on tiles that straddle the row's key limit
@@ -251,24 +257,28 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const float sub = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
       float rs = 0.f;
-      // P (16-bit) into the SWIZZLE_128B K-major A-operand tile: row rl at rl*128 B, 16-byte chunk c stored at c ^ (rl & 7)
+      // P (16-bit) packed in registers while PV_{j-1} may still be running
+      uint32_t w[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int i = q * 2;
+        const float e0 = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), p.scale_log2e, -sub));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), p.scale_log2e, -sub));
+        rs += e0 + e1;
+        w[q] = pack2_16(e0, e1, p.fp16 != 0);
+      }
+      if (j > 0) {                                                        // PV_{j-1} retired: O stable, P tile free
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // into the SWIZZLE_128B K-major A-operand tile: row rl at rl*128 B, 16-byte chunk c stored at c ^ (rl & 7)
       uint8_t* prow = p_ptr + rl * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int i = c * 8 + q * 2;
-          const float e0 = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), p.scale_log2e, -sub));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), p.scale_log2e, -sub));
-          rs += e0 + e1;
-          w[q] = pack2_16(e0, e1, p.fp16 != 0);
-        }
-        *reinterpret_cast<uint4*>(prow + ((c ^ (rl & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (rl & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
       l_run = l_run * corr + rs;
       m_run = m_new;
-      // rescale O only when some row of this warp moved its maximum (PV_{j-1} has retired: s_full(j) was committed after it)
+      // rescale O only when some row of this warp moved its maximum
       if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
         tmem_ld32(o_tmem + lane_addr, r0);
         tmem_ld32(o_tmem + lane_addr + 32, r1);
@@ -288,7 +298,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       if (lane == 0) mbar_arrive(p_ready);
     }
     // ---- epilogue: O / l -> 16-bit planes (A operand of the proj GEMM) and / or fp32
-    mbar_wait(o_final, 0);
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
     tc_fence_after();
     uint32_t r0[32], r1[32];
     tmem_ld32(o_tmem + lane_addr, r0);

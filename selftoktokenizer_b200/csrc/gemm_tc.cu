@@ -128,19 +128,37 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, int fp16) {
 constexpr int EPI_STAGE_FLOATS = 32 * 32;
 constexpr int EPI_WARPS = 8;
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// two fp32 -> packed 16-bit pair (IEEE half, saturating, or bf16): one cvt per pair
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, bool fp16) {
+  uint32_t r;
+  if (fp16) {
+    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
+  return r;
+}
+// MODE / GELU are compile-time so that the per-element path carries no mode branches; the arithmetic of all 8 row passes
+// of a chunk is issued unconditionally (independent chains -> ILP) and only the global stores are predicated.
+template <int MODE, bool GELU>
 __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_addr, float* stage, int lane,
                                                int64_t m_base, int64_t M, int n_first, int N) {
   const int rsub = lane >> 3, cq = lane & 7;            // pass k: row 4k + rsub of the chunk; this lane's 4 columns
-  const bool per_row_gate = e.mode == EPI_RESID && e.gate && e.gate_period > 1;
-  const bool per_row_add = e.mode == EPI_STORE && e.addtab;
-  int orow[8], mrow[8];
+  const bool per_row_gate = MODE == EPI_RESID && e.gate && e.gate_period > 1;
+  const bool per_row_add = MODE == EPI_STORE && e.addtab;
+  const bool fp16 = e.fp16 != 0;
+  int64_t obase[8];
+  int mrow[8];
   bool rvalid[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int64_t m = m_base + 4 * k + rsub;
     rvalid[k] = m < M;
     const int mi = (int)m;
-    orow[k] = e.rpb_in > 0 ? (mi / e.rpb_in) * e.rpb_out + e.row_off + (mi % e.rpb_in) : mi;
+    const int orow = e.rpb_in > 0 ? (mi / e.rpb_in) * e.rpb_out + e.row_off + (mi % e.rpb_in) : mi;
+    obase[k] = (int64_t)orow * e.ldo;
     mrow[k] = per_row_gate ? mi % e.gate_period : (per_row_add ? mi % e.add_period : 0);
   }
 #pragma unroll 1
@@ -152,12 +170,12 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 bias = (e.bias && col_ok) ? ldg4(e.bias + n) : zero4;
     float4 res[8], gt[8];
-    if (e.mode == EPI_RESID) {
+    if (MODE == EPI_RESID) {
       const float4 g0 = (e.gate && !per_row_gate && col_ok) ? ldg4(e.gate + n) : make_float4(1.f, 1.f, 1.f, 1.f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const bool ok = col_ok && rvalid[k];
-        res[k] = ok ? ldg4(e.resid + (int64_t)orow[k] * e.ldo + n) : zero4;
+        res[k] = ok ? ldg4(e.resid + obase[k] + n) : zero4;
         gt[k] = (per_row_gate && ok) ? ldg4(e.gate + (int64_t)mrow[k] * e.gate_ld + n) : g0;
       }
     }
@@ -169,34 +187,53 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<uint4*>(&stage[lane * 32 + ((q ^ (lane & 7)) << 2)]) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     __syncwarp();
+    float4 y[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int row = 4 * k + rsub;
-      if (!(col_ok && rvalid[k])) continue;
-      float4 v = *reinterpret_cast<const float4*>(&stage[row * 32 + ((cq ^ (row & 7)) << 2)]);
-      float y[4] = {v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w};
-      if (e.act == ACT_GELU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = gelu_tanh_fast(y[j]);
-      } else if (e.act == ACT_SILU) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = silu(y[j]);
+      const float4 v = *reinterpret_cast<const float4*>(&stage[row * 32 + ((cq ^ (row & 7)) << 2)]);
+      y[k] = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
+      if (GELU) {
+        y[k].x = gelu_tanh_fast(y[k].x); y[k].y = gelu_tanh_fast(y[k].y);
+        y[k].z = gelu_tanh_fast(y[k].z); y[k].w = gelu_tanh_fast(y[k].w);
       }
-      const int64_t o = (int64_t)orow[k] * e.ldo + n;
-      if (e.mode == EPI_STORE) {
-        if (per_row_add) { const float4 a = ldg4(e.addtab + (int64_t)mrow[k] * e.add_ld + n); y[0] += a.x; y[1] += a.y; y[2] += a.z; y[3] += a.w; }
-        *reinterpret_cast<float4*>(e.out + o) = make_float4(y[0], y[1], y[2], y[3]);
-      } else if (e.mode == EPI_RESID) {
-        *reinterpret_cast<float4*>(e.out + o) = make_float4(res[k].x + gt[k].x * y[0], res[k].y + gt[k].y * y[1],
-                                                            res[k].z + gt[k].z * y[2], res[k].w + gt[k].w * y[3]);
-      } else {
-        uint16_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split16(y[j], e.fp16, h[j], l[j]);
-        *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(h[0] | ((uint32_t)h[1] << 16), h[2] | ((uint32_t)h[3] << 16));
-        if (e.out_lo) *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(l[0] | ((uint32_t)l[1] << 16), l[2] | ((uint32_t)l[3] << 16));
+      if (MODE == EPI_RESID) {
+        y[k].x = fmaf(gt[k].x, y[k].x, res[k].x); y[k].y = fmaf(gt[k].y, y[k].y, res[k].y);
+        y[k].z = fmaf(gt[k].z, y[k].z, res[k].z); y[k].w = fmaf(gt[k].w, y[k].w, res[k].w);
       }
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (!(col_ok && rvalid[k])) continue;
+      const int64_t o = obase[k] + n;
+      if (MODE == EPI_SPLIT) {
+        *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(pack2(y[k].x, y[k].y, fp16), pack2(y[k].z, y[k].w, fp16));
+        if (e.out_lo) {                                  // bf16x3: residual planes
+          const float lx = y[k].x - __bfloat162float(__float2bfloat16_rn(y[k].x)), ly = y[k].y - __bfloat162float(__float2bfloat16_rn(y[k].y));
+          const float lz = y[k].z - __bfloat162float(__float2bfloat16_rn(y[k].z)), lw = y[k].w - __bfloat162float(__float2bfloat16_rn(y[k].w));
+          *reinterpret_cast<uint2*>(e.out_lo + o) = make_uint2(pack2(lx, ly, false), pack2(lz, lw, false));
+        }
+      } else {
+        if (per_row_add) {
+          const float4 a = ldg4(e.addtab + (int64_t)mrow[k] * e.add_ld + n);
+          y[k].x += a.x; y[k].y += a.y; y[k].z += a.z; y[k].w += a.w;
+        }
+        *reinterpret_cast<float4*>(e.out + o) = y[k];
+      }
+    }
+  }
+}
+
+// mode / activation dispatch (uniform across the grid)
+__device__ __forceinline__ void epilogue_dispatch(const Epilogue& e, uint32_t tmem_addr, float* stage, int lane, int64_t m_base,
+                                                  int64_t M, int n_first, int N) {
+  if (e.mode == EPI_RESID) epilogue_block<EPI_RESID, false>(e, tmem_addr, stage, lane, m_base, M, n_first, N);
+  else if (e.mode == EPI_SPLIT) {
+    if (e.act == ACT_GELU) epilogue_block<EPI_SPLIT, true>(e, tmem_addr, stage, lane, m_base, M, n_first, N);
+    else epilogue_block<EPI_SPLIT, false>(e, tmem_addr, stage, lane, m_base, M, n_first, N);
+  } else {
+    if (e.act == ACT_GELU) epilogue_block<EPI_STORE, true>(e, tmem_addr, stage, lane, m_base, M, n_first, N);
+    else epilogue_block<EPI_STORE, false>(e, tmem_addr, stage, lane, m_base, M, n_first, N);
   }
 }
 
@@ -330,7 +367,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_block(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
+      epilogue_dispatch(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
                      (int64_t)m_blk * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
       tc_fence_before();
       __syncwarp();
@@ -523,7 +560,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      epilogue_block(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
+      epilogue_dispatch(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
                      (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
       tc_fence_before();
       __syncwarp();
@@ -611,6 +648,8 @@ int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const _
   STK_CHECK(A_hi && W_hi && M > 0 && N > 0 && K > 0, -1, "gemm_tc: bad arguments");
   STK_CHECK(nsplit == 1 || (nsplit == 3 && A_lo && W_lo), -1, "gemm_tc: nsplit must be 1, or 3 with lo planes");
   STK_CHECK(!fp16 || nsplit == 1, -1, "gemm_tc: the fp16 mode is single-pass");
+  STK_CHECK(ep.act == ACT_NONE || (ep.act == ACT_GELU && ep.mode != EPI_RESID), -2,
+            "gemm_tc: epilogue activation must be none, or GELU-tanh with the store / split modes");
   STK_CHECK(ep.mode != EPI_STORE || ep.addtab == nullptr || ep.add_ld % 4 == 0, -2, "gemm_tc: addtab pitch must be a multiple of 4");
   STK_CHECK(K % 8 == 0, -2, "gemm_tc: K must be a multiple of 8 (16-byte TMA row pitch)");
   STK_CHECK(ep.ldo % 4 == 0 && N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");

@@ -87,7 +87,7 @@ def _decoder_state(state_dict: Dict, ema_decoder: bool) -> Dict[str, torch.Tenso
 class SelftokPipeline:
     def __init__(self, cfg, ckpt_path, sd3_path, datasize=256, start=1.0, cfg_scale=1, model_type="sd3",
                  dtype=torch.bfloat16, ema_decoder=False, device=None, *, state_dict=None, vae=None,
-                 precision="fp16", dims: Optional[SelftokDims] = None):
+                 precision="auto", dims: Optional[SelftokDims] = None):
         self.cfg = cfg
         self.datasize = datasize
         self.model_type = model_type

@@ -50,17 +50,17 @@ def test_no_cpu_fallback():
 
 
 def test_config_surface():
-    cfg = C.parse_args_from_yaml(os.path.join(REPO, "configs/res256/256-eval.yml"))
+    cfg = C.parse_args_from_yaml(os.path.join(REPO, "configs/selftok_256_512tok.yml"))
     assert cfg.tokenizer.params.k == 512 and cfg.common.is_eval is True
     assert not hasattr(cfg.tokenizer.params, "cut_of_k")
     before = repr(cfg)
     d = C.SelftokDims.from_cfg(cfg)
     assert repr(cfg) == before, "from_cfg must not mutate cfg (the reference does; consciously dropped)"
     assert d == C.FULL and d.dit_hidden == 1536 and d.n_img == 256 and d.enc_n_img == 256
-    r = C.SelftokDims.from_cfg(C.parse_args_from_yaml(os.path.join(REPO, "configs/renderer/renderer-eval.yml")))
+    r = C.SelftokDims.from_cfg(C.parse_args_from_yaml(os.path.join(REPO, "configs/selftok_renderer_512tok.yml")))
     assert r.renderer and not r.context_see_xt and r.stages == (1000,)
     with pytest.raises(KeyError):
-        bad = C.parse_args_from_yaml(os.path.join(REPO, "configs/res256/256-eval.yml"))
+        bad = C.parse_args_from_yaml(os.path.join(REPO, "configs/selftok_256_512tok.yml"))
         bad.tokenizer.params.enc = "Enc-Qformer-Uni-L/2"
         C.SelftokDims.from_cfg(bad)
 

@@ -110,7 +110,8 @@ def test_pipeline_api_latent_boundary(tiny_sd, gold):
     g = gold("tiny")
     d = C.TINY
     pipe = SelftokPipeline(cfg=None, ckpt_path=None, sd3_path=None, datasize=d.latent * 8, device=DEV, state_dict=tiny_sd,
-                           dims=d, precision="bf16x3")
+                           dims=d)
+    assert pipe.engine.precision == "fp16"                            # "auto": half operands for the 50-step sampler
     assert pipe.K == d.K and pipe._steps == 50 and pipe.cond_vary is True and pipe.cfg_scale == 1
     x0 = synth.synth_tensor("golden.tiny.x0", (3, d.in_channels, d.latent, d.latent), "emb", 1.0)
     tokens = pipe.encode_latents(x0)
@@ -119,7 +120,7 @@ def test_pipeline_api_latent_boundary(tiny_sd, gold):
     _check_tokens(idx, g["tokens"], g["margin"], "pipeline encode")
     torch.manual_seed(1234)                                           # the reference draws the noise on the CPU generator
     x = pipe.decode_latents(g["tokens"])
-    assert np.abs(x.cpu().numpy() - g["pred_x0"]).max() < TOL["bf16x3"]
+    assert np.abs(x.cpu().numpy() - g["pred_x0"]).max() < TOL["fp16"]
     with pytest.raises(SelftokError):
         pipe.decoding(idx, DEV)                                        # pixel API needs the SD3 VAE
 
@@ -172,6 +173,29 @@ def test_full_decode_50_steps(full_engine, gold):
     assert err < 1e-3
 
 
+def test_full_renderer_one_pass(gold):
+    """decoding_with_renderer at the shipped geometry (BASELINE config[3], 512-token renderer YAML): one MMDiT_Renderer pass."""
+    from selftoktokenizer_b200.capi import Engine
+    g = gold("full_renderer")
+    ge = gold("full_encode")
+    d = dataclasses.replace(C.FULL, renderer=True)
+    # "auto" resolves to bf16x3 for the renderer: its output is ONE network evaluation, so single-pass half operands land at
+    # the edge of the 1e-3 bar (measured 1.05e-3) instead of averaging out as in the 50-step sampler; fp16 is reported only.
+    for precision, tol in (("auto", 1e-3), ("fp16", 2.5e-3)):
+        eng = Engine(d, synth.synth_state_dict(d, device=DEV), device=DEV, precision=precision)
+        precision = eng.precision
+        r = eng.render(torch.from_numpy(ge["tokens"][:1])).cpu().numpy()
+        err = np.abs(r - g["pred_x0"]).max()
+        ref = g["pred_x0"]
+        psnr_drop = 10 * np.log10(((ref.max() - ref.min()) ** 2) / max(((r - ref) ** 2).mean(), 1e-30))
+        print(f"[{precision}] full-geometry renderer: max-abs err {err:.3e}; PSNR of ours vs reference {psnr_drop:.1f} dB")
+        assert err < tol
+        out = torch.empty(1, d.in_channels, d.latent, d.latent).pin_memory()
+        eng.render_host(torch.from_numpy(ge["tokens"][:1]).pin_memory(), out)
+        assert np.array_equal(out.numpy(), r)
+        eng.close()
+
+
 def test_full_batch_roundtrip_properties(full_engine):
     """BASELINE-size property checks the CPU oracle cannot reach (B=64 encode): determinism, shard invariance,
     ids in range, and encode -> lookup -> VQ idempotence (re-quantising a code returns the same id)."""
@@ -186,3 +210,7 @@ def test_full_batch_roundtrip_properties(full_engine):
     ids, _ = full_engine.vq_argmax(feats)
     assert torch.equal(ids.reshape(tok.shape), tok)
     assert (tok[0] != tok[1]).float().mean() > 0.3
+    # host-buffer entry == device entry
+    tok_h = torch.empty(64, d.K, dtype=torch.int64).pin_memory()
+    full_engine.encode_host(x0.cpu().pin_memory(), tok_h)
+    assert torch.equal(tok_h, tok.cpu())
