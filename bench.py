@@ -275,7 +275,7 @@ def run_gpu(args):
             g_ms, g_n = prof["gemm_tcgen05"]
             flops = gemm_flops_per_step(B)
             ach = flops / (g_ms / 1000.0) / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 kind::f16, %s)" % args.precision,
+            roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 kind::f16, %s)" % args.precision,
                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
                     "traffic": None, "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,

@@ -251,22 +251,29 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           if (k0 + 32 + i >= kmax) r1[i] = 0xff800000u;
         }
       }
+      {                                                                   // 8 independent chains instead of one of 64
+        float mp[8];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        for (int i = 0; i < 8; ++i) mp[i] = fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i]));
+#pragma unroll
+        for (int i = 8; i < 32; ++i) mp[i & 7] = fmaxf(mp[i & 7], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+        mx = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])), fmaxf(fmaxf(mp[4], mp[5]), fmaxf(mp[6], mp[7])));
+      }
       const float m_new = fmaxf(m_run, mx * p.scale_log2e);
       const float sub = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-      float rs = 0.f;
-      // P (16-bit) packed in registers while PV_{j-1} may still be running
+      // P (16-bit) packed in registers while PV_{j-1} may still be running; 4 independent partial row sums
       uint32_t w[32];
+      float rsp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int q = 0; q < 32; ++q) {
         const int i = q * 2;
         const float e0 = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), p.scale_log2e, -sub));
         const float e1 = ex2_approx(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), p.scale_log2e, -sub));
-        rs += e0 + e1;
+        rsp[q & 3] += e0 + e1;
         w[q] = pack2_16(e0, e1, p.fp16 != 0);
       }
+      const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
       if (j > 0) {                                                        // PV_{j-1} retired: O stable, P tile free
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();

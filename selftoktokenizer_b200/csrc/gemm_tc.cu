@@ -224,6 +224,27 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
   }
 }
 
+// Issued by the epilogue warps BEFORE they wait for the accumulator: pulls this warp's 32 x 128 residual block (and its
+// per-row gate rows) into L2 while the MMAs of the tile are still running, so the gated-residual loads of the epilogue hit L2
+// instead of paying the HBM latency once per chunk (long-scoreboard stalls were 37 % of the epilogue's samples).
+__device__ __forceinline__ void epilogue_prefetch(const Epilogue& e, int lane, int64_t m_base, int64_t M, int n_first, int N) {
+  if (e.mode != EPI_RESID) return;
+  const int64_t m = m_base + lane;
+  if (m >= M || n_first >= N) return;
+  const int mi = (int)m;
+  const int orow = e.rpb_in > 0 ? (mi / e.rpb_in) * e.rpb_out + e.row_off + (mi % e.rpb_in) : mi;
+  const float* rp = e.resid + (int64_t)orow * e.ldo + n_first;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (n_first + j * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * 32));
+  if (e.gate && e.gate_period > 1) {
+    const float* gp = e.gate + (int64_t)(mi % e.gate_period) * e.gate_ld + n_first;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n_first + j * 32 < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + j * 32));
+  }
+}
+
 // mode / activation dispatch (uniform across the grid)
 __device__ __forceinline__ void epilogue_dispatch(const Epilogue& e, uint32_t tmem_addr, float* stage, int lane, int64_t m_base,
                                                   int64_t M, int n_first, int N) {
@@ -365,6 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       tile_coords(t, m_tiles, n_tiles, m_blk, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      epilogue_prefetch(e, lane, (int64_t)m_blk * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       epilogue_dispatch(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
@@ -558,6 +580,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
       pair_coords(t, pm_tiles, n_tiles, pm, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      epilogue_prefetch(e, lane, (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       epilogue_dispatch(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
