@@ -61,6 +61,54 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
   const float u = k0 * (x + k1 * x * x * x);
   return __fdividef(x, 1.0f + __expf(-2.0f * u));
 }
+// GELU-tanh on a float4 with Blackwell's packed fp32 pipe (fma/mul/add .f32x2: two lanes per instruction):
+// y = x / (1 + 2^(c2 * x * (1 + k1 x^2))),  c2 = -2 log2(e) sqrt(2/pi); ex2 / rcp stay scalar MUFU ops.
+__device__ __forceinline__ float4 gelu_tanh_fast4(float4 v) {
+  const float k1 = 0.044715f, c2 = -2.0f * 1.4426950408889634f * 0.7978845608028654f;
+  float4 y;
+  asm("{\n\t"
+      ".reg .b64 xa, xb, ta, tb, ka, ca, one;\n\t"
+      ".reg .f32 e0, e1, e2, e3;\n\t"
+      "mov.b64 xa, {%4, %5};\n\t"
+      "mov.b64 xb, {%6, %7};\n\t"
+      "mov.b64 ka, {%8, %8};\n\t"
+      "mov.b64 ca, {%9, %9};\n\t"
+      "mov.b64 one, {%10, %10};\n\t"
+      "mul.f32x2 ta, xa, xa;\n\t"            // x^2
+      "mul.f32x2 tb, xb, xb;\n\t"
+      "fma.rn.f32x2 ta, ta, ka, one;\n\t"    // 1 + k1 x^2
+      "fma.rn.f32x2 tb, tb, ka, one;\n\t"
+      "mul.f32x2 ta, ta, xa;\n\t"            // x (1 + k1 x^2)
+      "mul.f32x2 tb, tb, xb;\n\t"
+      "mul.f32x2 ta, ta, ca;\n\t"            // exponent (base 2)
+      "mul.f32x2 tb, tb, ca;\n\t"
+      "mov.b64 {e0, e1}, ta;\n\t"
+      "mov.b64 {e2, e3}, tb;\n\t"
+      "ex2.approx.ftz.f32 e0, e0;\n\t"
+      "ex2.approx.ftz.f32 e1, e1;\n\t"
+      "ex2.approx.ftz.f32 e2, e2;\n\t"
+      "ex2.approx.ftz.f32 e3, e3;\n\t"
+      "mov.b64 ta, {e0, e1};\n\t"
+      "mov.b64 tb, {e2, e3};\n\t"
+      "add.f32x2 ta, ta, one;\n\t"           // 1 + e
+      "add.f32x2 tb, tb, one;\n\t"
+      "mov.b64 {e0, e1}, ta;\n\t"
+      "mov.b64 {e2, e3}, tb;\n\t"
+      "rcp.approx.ftz.f32 e0, e0;\n\t"
+      "rcp.approx.ftz.f32 e1, e1;\n\t"
+      "rcp.approx.ftz.f32 e2, e2;\n\t"
+      "rcp.approx.ftz.f32 e3, e3;\n\t"
+      "mov.b64 ta, {e0, e1};\n\t"
+      "mov.b64 tb, {e2, e3};\n\t"
+      "mul.f32x2 ta, ta, xa;\n\t"            // x / (1 + e)
+      "mul.f32x2 tb, tb, xb;\n\t"
+      "mov.b64 {%0, %1}, ta;\n\t"
+      "mov.b64 {%2, %3}, tb;\n\t"
+      "}"
+      : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w)
+      : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(k1), "f"(c2), "f"(1.0f));
+  return y;
+}
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
 enum Act { ACT_NONE = 0, ACT_GELU = 1, ACT_SILU = 2 };

@@ -193,10 +193,7 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
       const int row = 4 * k + rsub;
       const float4 v = *reinterpret_cast<const float4*>(&stage[row * 32 + ((cq ^ (row & 7)) << 2)]);
       y[k] = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
-      if (GELU) {
-        y[k].x = gelu_tanh_fast(y[k].x); y[k].y = gelu_tanh_fast(y[k].y);
-        y[k].z = gelu_tanh_fast(y[k].z); y[k].w = gelu_tanh_fast(y[k].w);
-      }
+      if (GELU) y[k] = gelu_tanh_fast4(y[k]);
       if (MODE == EPI_RESID) {
         y[k].x = fmaf(gt[k].x, y[k].x, res[k].x); y[k].y = fmaf(gt[k].y, y[k].y, res[k].y);
         y[k].z = fmaf(gt[k].z, y[k].z, res[k].z); y[k].w = fmaf(gt[k].w, y[k].w, res[k].w);
