@@ -7,9 +7,10 @@
 //   warp 1         MMA issuer (one thread):  S = Q K^T  -> TMEM cols [0,64) / [64,128) (UMMA 128x64x16 x4, both operands K-major)
 //                                            O += P V   -> TMEM cols [128,192)      (UMMA 128x64x16 x4, A = P K-major from smem,
 //                                                                              B = V MN-major straight from the TMA tile)
-//   warps 2-5      one thread per query row (TMEM lane): tcgen05.ld the row of S, online softmax in registers (no
-//                  shuffles), rescale its row of O in TMEM (tcgen05.ld / tcgen05.st), write P as 16-bit into the
-//                  SWIZZLE_128B A-operand tile, finally normalise O and store it as the A-operand planes of the proj GEMM
+//   warps 2-9      two threads per query row (TMEM lane quarter = warp % 4, 32 of the 64 keys / dims each): tcgen05.ld the
+//                  half row of S, online softmax in registers (row max exchanged through smem, no shuffles), rescale the
+//                  half row of O in TMEM (tcgen05.ld / tcgen05.st), write P as 16-bit into the SWIZZLE_128B A-operand tile,
+//                  finally normalise O and store it as the A-operand planes of the proj GEMM
 //
 // Same contract as attn_tc.cu (sd3/mmdit.py:521-531, sd3/other_impls.py:37-45): dense non-causal attention over the joint
 // [context prefix ; image] sequence; rows < ctx_rows only see keys < ctx_keys (renderer rule, mmdit.py:1581).
@@ -28,10 +29,11 @@ namespace {
 
 constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 3;
 constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2, P_BYTES = BQ * BKV * 2;
-constexpr int SMEM_TILES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES;      // 16 + 48 + 16 = 80 KiB
-constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 128;
+constexpr int SMEM_TILES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 16 + 48 + 2 x 16 = 96 KiB (P double-buffered)
+constexpr int XCH_BYTES = 6 * BQ * 4;               // row-max exchange (2 parities x 2 halves) + partial-sum exchange (2 halves)
+constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 128 + XCH_BYTES;
 constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O [128,192)
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 64 + 8 * 32;        // TMA warp, MMA warp, 8 softmax warps
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -143,6 +145,7 @@ struct Attn5Params {
   float scale_log2e;
 };
 
+template <bool FP16>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,12 +153,16 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const uint32_t q_s = base;
   const uint32_t kv_s = base + Q_BYTES;                       // stage st: K at kv_s + st*2*KV_TILE_BYTES, V right after
   const uint32_t p_s = kv_s + KV_STAGES * 2 * KV_TILE_BYTES;
-  const uint32_t bars = p_s + P_BYTES;
-  const uint32_t q_full = bars, p_ready = bars + 8, pv_done = bars + 16;
-  auto s_full = [&](int sb) { return bars + 24 + 8u * sb; };
-  auto kv_full = [&](int st) { return bars + 40 + 8u * st; };
-  auto kv_empty = [&](int st) { return bars + 64 + 8u * st; };
-  const uint32_t tmem_slot = bars + 96;
+  const uint32_t bars = p_s + 2 * P_BYTES;
+  // every per-tile barrier exists twice (tile parity) so that no waiter can be lapped by two phases
+  const uint32_t q_full = bars;
+  auto p_ready = [&](int pb) { return bars + 8 + 8u * pb; };
+  auto pv_done = [&](int pb) { return bars + 24 + 8u * pb; };
+  auto s_full = [&](int sb) { return bars + 40 + 8u * sb; };
+  auto kv_full = [&](int st) { return bars + 56 + 8u * st; };
+  auto kv_empty = [&](int st) { return bars + 80 + 8u * st; };
+  const uint32_t tmem_slot = bars + 104;
+  const uint32_t xch_s = bars + 128;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   uint8_t* p_ptr = smem_raw + (p_s - smem_u32(smem_raw));
 
@@ -166,7 +173,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   const int n_tiles = (kmax_cta + BKV - 1) / BKV;
 
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(s_full(0), 1); mbar_init(s_full(1), 1); mbar_init(p_ready, 4); mbar_init(pv_done, 1);
+    mbar_init(q_full, 1); mbar_init(s_full(0), 1); mbar_init(s_full(1), 1);
+    mbar_init(p_ready(0), 8); mbar_init(p_ready(1), 8); mbar_init(pv_done(0), 1); mbar_init(pv_done(1), 1);
     for (int st = 0; st < KV_STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -199,8 +207,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   } else if (warp == 1) {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc(BQ, BKV, p.fp16, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
-      const uint32_t idesc_pv = make_idesc(BQ, HD, p.fp16, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
+      const uint32_t idesc_qk = make_idesc(BQ, BKV, FP16 ? 1 : 0, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
+      const uint32_t idesc_pv = make_idesc(BQ, HD, FP16 ? 1 : 0, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
       mbar_wait(q_full, 0);
       auto issue_qk = [&](int j) {                                       // S[j & 1] = Q K_j^T
         const int st = j % KV_STAGES;
@@ -217,99 +225,99 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (j + 1 < n_tiles) issue_qk(j + 1);                            // overlaps the softmax of tile j (S is double-buffered)
         const int st = j % KV_STAGES;
         const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
-        mbar_wait(p_ready, j & 1);                                       // P_j in smem, O rescaled, S[j & 1] consumed
+        mbar_wait(p_ready(j & 1), (j >> 1) & 1);                         // P_j in smem, O rescaled, S[j & 1] consumed
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)                               // K dimension = keys: 16 keys = 2 atoms of 8 key rows
-          tc_mma_f16(o_tmem, make_smem_desc(p_s + k * 32), make_smem_desc(vs + k * 2048), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          tc_mma_f16(o_tmem, make_smem_desc(p_s + (j & 1) * P_BYTES + k * 32), make_smem_desc(vs + k * 2048), idesc_pv,
+                     (j > 0 || k > 0) ? 1u : 0u);
         tc_commit(kv_empty(st));                                         // K/V stage reusable once QK_j and PV_j retire
-        tc_commit(pv_done);                                              // O and the P tile are free again
+        tc_commit(pv_done(j & 1));                                       // P[j & 1] free again; O holds tiles 0..j
       }
     }
   } else {
-    // =========================================================== softmax / correction / epilogue: thread = query row
-    const int quarter = warp & 3;
+    // =========================================================== softmax / correction / epilogue
+    // 8 warps: TMEM lane quarter = warp % 4 (hardware rule), column half = (warp - 2) / 4.  Two threads share a query row,
+    // each owning 32 of the tile's 64 keys (and 32 of the 64 output dims); they exchange only the row maximum per tile
+    // (shared memory + a 64-thread named barrier); the row sums stay partial until the end.  Twice the warps of the
+    // thread-per-row version hide the fixed-latency stalls of the exp / convert chain.
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int rl = quarter * 32 + lane;                                  // row inside the tile = TMEM lane
     const int row = q0 + rl;
     const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
+    float* xch = reinterpret_cast<float*>(smem_raw + (xch_s - smem_u32(smem_raw)));   // [2 halves][128 rows]
+    float m_run = -INFINITY, l_part = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full(j & 1), (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(s_tmem0 + 64 * (j & 1) + lane_addr, r0);
-      tmem_ld32(s_tmem0 + 64 * (j & 1) + lane_addr + 32, r1);
+      uint32_t r0[32];
+      tmem_ld32(s_tmem0 + 64 * (j & 1) + 32 * half + lane_addr, r0);
       tmem_ld_wait();
-      const int k0 = j * BKV;
-      // row maximum on the raw scores (the scale is positive); masking only on tiles that straddle the row's key limit
-      float mx = -INFINITY;
-      if (k0 + BKV > kmax) {                                              // thread-level branch, no collectives inside
+      const int k0 = j * BKV + 32 * half;
+      if (k0 + 32 > kmax) {                                               // tile straddles this row's key limit
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < 32; ++i)
           if (k0 + i >= kmax) r0[i] = 0xff800000u;                        // -inf
-          if (k0 + 32 + i >= kmax) r1[i] = 0xff800000u;
-        }
       }
-      {                                                                   // 8 independent chains instead of one of 64
-        float mp[8];
+      float mx;
+      {
+        float mp[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mp[i] = fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i]));
+        for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
 #pragma unroll
-        for (int i = 8; i < 32; ++i) mp[i & 7] = fmaxf(mp[i & 7], fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-        mx = fmaxf(fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])), fmaxf(fmaxf(mp[4], mp[5]), fmaxf(mp[6], mp[7])));
+        for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
+        mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
       }
+      // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
+      xch[((j & 1) * 2 + half) * BQ + rl] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * BQ + rl]);
       const float m_new = fmaxf(m_run, mx * p.scale_log2e);
       const float sub = (m_new == -INFINITY) ? 0.f : m_new;
       const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-      // P (16-bit) packed in registers while PV_{j-1} may still be running; 4 independent partial row sums
-      uint32_t w[32];
+      uint32_t w[16];
       float rsp[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        const int i = q * 2;
-        const float e0 = ex2_approx(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), p.scale_log2e, -sub));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), p.scale_log2e, -sub));
+      for (int q = 0; q < 16; ++q) {
+        const float e0 = ex2_approx(fmaf(__uint_as_float(r0[2 * q]), p.scale_log2e, -sub));
+        const float e1 = ex2_approx(fmaf(__uint_as_float(r0[2 * q + 1]), p.scale_log2e, -sub));
         rsp[q & 3] += e0 + e1;
-        w[q] = pack2_16(e0, e1, p.fp16 != 0);
+        w[q] = pack2_16(e0, e1, FP16);
       }
       const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
-      if (j > 0) {                                                        // PV_{j-1} retired: O stable, P tile free
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
-      // into the SWIZZLE_128B K-major A-operand tile: row rl at rl*128 B, 16-byte chunk c stored at c ^ (rl & 7)
-      uint8_t* prow = p_ptr + rl * 128;
+      if (j > 1) mbar_wait(pv_done(j & 1), ((j - 2) >> 1) & 1);          // PV_{j-2} retired: P[j & 1] is free
+      // this thread's 32 keys = 16-byte chunks 4*half .. 4*half+3 of row rl in the SWIZZLE_128B K-major A tile
+      uint8_t* prow = p_ptr + (j & 1) * P_BYTES + rl * 128;
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(prow + ((c ^ (rl & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-      l_run = l_run * corr + rs;
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(prow + (((4 * half + c) ^ (rl & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+      l_part = l_part * corr + rs;
       m_run = m_new;
-      // rescale O only when some row of this warp moved its maximum
+      // rescale this thread's 32 output dims only when some row of the warp moved its maximum
       if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
-        tmem_ld32(o_tmem + lane_addr, r0);
-        tmem_ld32(o_tmem + lane_addr + 32, r1);
+        mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);              // PV_{j-1} retired: O is stable
+        tc_fence_after();
+        tmem_ld32(o_tmem + 32 * half + lane_addr, r0);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
-          r1[i] = __float_as_uint(__uint_as_float(r1[i]) * corr);
-        }
-        tmem_st32(o_tmem + lane_addr, r0);
-        tmem_st32(o_tmem + lane_addr + 32, r1);
+        for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
+        tmem_st32(o_tmem + 32 * half + lane_addr, r0);
         tmem_st_wait();
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // st.shared of P -> visible to the tensor core
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(p_ready(j & 1));
     }
-    // ---- epilogue: O / l -> 16-bit planes (A operand of the proj GEMM) and / or fp32
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    // ---- epilogue: combine the partial row sums, O / l -> 16-bit planes (A operand of the proj GEMM) and / or fp32
+    xch[(4 + half) * BQ + rl] = l_part;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+    const float l_run = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
+    mbar_wait(pv_done((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
-    uint32_t r0[32], r1[32];
-    tmem_ld32(o_tmem + lane_addr, r0);
-    tmem_ld32(o_tmem + lane_addr + 32, r1);
+    uint32_t r0[32];
+    tmem_ld32(o_tmem + 32 * half + lane_addr, r0);
     tmem_ld_wait();
     if (row < S) {
       const float inv = 1.0f / l_run;
@@ -319,15 +327,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       float* of = inA ? t.f32_a : t.f32_b;
       uint16_t* oh = reinterpret_cast<uint16_t*>(inA ? t.hi_a : t.hi_b);
       uint16_t* ol = reinterpret_cast<uint16_t*>(inA ? t.lo_a : t.lo_b);
-      const int64_t o = orow * t.ld + (int64_t)h * HD;
+      const int64_t o = orow * t.ld + (int64_t)h * HD + 32 * half;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         float y[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int i = c * 8 + q;
-          y[q] = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) * inv;
-        }
+        for (int q = 0; q < 8; ++q) y[q] = __uint_as_float(r0[c * 8 + q]) * inv;
         if (of) {
           *reinterpret_cast<float4*>(of + o + c * 8) = make_float4(y[0], y[1], y[2], y[3]);
           *reinterpret_cast<float4*>(of + o + c * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
@@ -362,7 +367,8 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
   STK_TRY(gemm_tc_init());
   if (!g_attr_set) {
-    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_set = true;
   }
   CUtensorMap mq, mkv;
@@ -371,7 +377,8 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   STK_TRY(make_tensor_map_2d(&mkv, qkv16, rows, cols, BKV, HD, fp16));
   Attn5Params p{out, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
   dim3 grid((S + BQ - 1) / BQ, H, B);
-  attention_tc5_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  if (fp16) attention_tc5_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  else attention_tc5_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;
