@@ -355,6 +355,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
     PROF(PC_OTHER, launch_crop_pos(pe->d, e->dit_pos, c.dit_pos_max, g, D, s));
   }
   // ---- tensor-core operand planes of the MMDiT linears
+  std::vector<std::string> packed_names;
   if (tc_mode(e)) {
     const char* blocks[2] = {"context_block", "x_block"};
     const char* lins[4] = {"attn.qkv", "attn.proj", "mlp.fc1", "mlp.fc2"};
@@ -369,10 +370,18 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
           if (nsplit(e) == 3) STK_TRY(dalloc(e, e->allocs, &p.lo, W->numel));
           PROF(PC_OTHER, launch_split_bf16(W->d, p.hi, p.lo, W->numel, s, is_fp16(e)));
           e->wp[name] = p;
+          packed_names.push_back(name);
         }
   }
   STK_CUDA(cudaStreamSynchronize(s));
   for (void* p : scratch) cudaFree(p);
+  // the fp32 staging copies of the packed MMDiT weights are not read again (their shapes are): release 8.3 GB
+  for (const std::string& name : packed_names) {
+    Tensor& t = e->w[name];
+    cudaFree(t.d);
+    t.d = nullptr;
+    e->bytes -= t.numel * 4;
+  }
   e->finalized = true;
   return SELFTOK_OK;
 }
