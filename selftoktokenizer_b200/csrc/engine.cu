@@ -162,6 +162,27 @@ static int lintc(selftok_engine* e, const std::string& prefix, const bf16* A_hi,
   return 0;
 }
 
+// tcgen05 problem descriptor for a checkpoint linear (weights already packed at finalize)
+static int tc_problem(selftok_engine* e, const std::string& prefix, const bf16* A_hi, const bf16* A_lo, int64_t M, Epilogue ep,
+                      TcProblem* out) {
+  GETW(W, prefix + ".weight");
+  GETW(Bv, prefix + ".bias");
+  auto it = e->wp.find(prefix + ".weight");
+  STK_CHECK(it != e->wp.end(), SELFTOK_ERR_STATE, "packed weight missing");
+  const int N = (int)W->shape[0];
+  const int K = (int)(W->numel / W->shape[0]);
+  ep.bias = Bv->d;
+  if (ep.ldo == 0) ep.ldo = N;
+  ep.fp16 = is_fp16(e);
+  *out = TcProblem{A_hi, A_lo, it->second.hi, it->second.lo, M, N, K, ep};
+  return 0;
+}
+// the context- and image-stream GEMM of a layer in ONE launch (n == 1: image stream only)
+static int lintc2(selftok_engine* e, const TcProblem* probs, int n, cudaStream_t s) {
+  PROF(PC_GEMM_TC, launch_gemm_tc_grouped(probs, n, nsplit(e), s, is_fp16(e)));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ C ABI: lifetime
 extern "C" __attribute__((visibility("default"))) const char* selftok_last_error(void) { return g_error.c_str(); }
 extern "C" __attribute__((visibility("default"))) const char* selftok_version(void) { return "selftok_b200 abi1 sm_100a (fp32-ffma + tcgen05 kind::f16)"; }
@@ -632,6 +653,54 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
     const std::string px = "model.joint_blocks." + std::to_string(j) + ".x_block.";
     const float* cmod = e->ctx_mod + (int64_t)j * c.K * 6 * D;                  // [K][6D]
     const float* xmod = e->x_mod + ((int64_t)j * T + step) * 6 * D;             // [6D]
+    if (tc_mode(e)) {
+      // ---- tensor-core path: the two streams' GEMMs of every stage share one launch (lintc2)
+      const int fp16 = is_fp16(e);
+      const float* lm = e->ctx_last_mod + (int64_t)step * 2 * D;                // last layer: pre_only (shift, scale) from c
+      if (!last) PROF(PC_LN, launch_ln_mod(w.ctx, D, cmod, cmod + D, 6 * D, Kc, nullptr, w.a_c_hi, w.a_c_lo, D, Mc, D, 1e-6f, s, fp16));
+      else PROF(PC_LN, launch_ln_mod(w.ctx, D, lm, lm + D, 2 * D, 1, nullptr, w.a_c_hi, w.a_c_lo, D, Mc, D, 1e-6f, s, fp16));
+      PROF(PC_LN, launch_ln_mod(w.x, D, xmod, xmod + D, 6 * D, 1, nullptr, w.a_x_hi, w.a_x_lo, D, Mx, D, 1e-6f, s, fp16));
+      TcProblem pr[2];
+      Epilogue eq;                                                              // q/k/v leave the GEMM as 16-bit planes in the joint buffer
+      eq.mode = EPI_SPLIT; eq.out_hi = w.qkv_hi; eq.out_lo = w.qkv_lo; eq.ldo = 3 * D; eq.rpb_out = S;
+      eq.rpb_in = Kc; eq.row_off = 0;
+      STK_TRY(tc_problem(e, pc + "attn.qkv", w.a_c_hi, w.a_c_lo, Mc, eq, &pr[0]));
+      eq.rpb_in = N; eq.row_off = Kc;
+      STK_TRY(tc_problem(e, px + "attn.qkv", w.a_x_hi, w.a_x_lo, Mx, eq, &pr[1]));
+      STK_TRY(lintc2(e, pr, 2, s));
+      AttnOut ao;
+      ao.split = Kc; ao.ld = D;
+      ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
+      ao.fp16 = fp16;
+      const int ctx_rows = ctx_self ? Kc : 0, ctx_keys = ctx_self ? Kc : 0;
+      if (nsplit(e) == 1 && e->attn_tcgen05)
+        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16));
+      else
+        PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, fp16));
+      // post_attention (mmdit.py:485-496); the pre_only context block of the last layer stops here
+      Epilogue erx, erc;
+      erx.mode = EPI_RESID; erx.out = w.x; erx.resid = w.x; erx.ldo = D; erx.gate = xmod + 2 * D; erx.gate_ld = 6 * D; erx.gate_period = 1;
+      erc.mode = EPI_RESID; erc.out = w.ctx; erc.resid = w.ctx; erc.ldo = D; erc.gate = cmod + 2 * D; erc.gate_ld = 6 * D; erc.gate_period = Kc;
+      int np = 0;
+      if (!last) STK_TRY(tc_problem(e, pc + "attn.proj", w.attn_c_hi, w.attn_c_lo, Mc, erc, &pr[np++]));
+      STK_TRY(tc_problem(e, px + "attn.proj", w.attn_x_hi, w.attn_x_lo, Mx, erx, &pr[np++]));
+      STK_TRY(lintc2(e, pr, np, s));
+      if (!last) PROF(PC_LN, launch_ln_mod(w.ctx, D, cmod + 3 * D, cmod + 4 * D, 6 * D, Kc, nullptr, w.a_c_hi, w.a_c_lo, D, Mc, D, 1e-6f, s, fp16));
+      PROF(PC_LN, launch_ln_mod(w.x, D, xmod + 3 * D, xmod + 4 * D, 6 * D, 1, nullptr, w.a_x_hi, w.a_x_lo, D, Mx, D, 1e-6f, s, fp16));
+      Epilogue ehc, ehx;
+      ehc.mode = EPI_SPLIT; ehc.act = ACT_GELU; ehc.out_hi = w.h_c_hi; ehc.out_lo = w.h_c_lo; ehc.ldo = 4 * D;
+      ehx = ehc; ehx.out_hi = w.h_x_hi; ehx.out_lo = w.h_x_lo;
+      np = 0;
+      if (!last) STK_TRY(tc_problem(e, pc + "mlp.fc1", w.a_c_hi, w.a_c_lo, Mc, ehc, &pr[np++]));
+      STK_TRY(tc_problem(e, px + "mlp.fc1", w.a_x_hi, w.a_x_lo, Mx, ehx, &pr[np++]));
+      STK_TRY(lintc2(e, pr, np, s));
+      erc.gate = cmod + 5 * D; erx.gate = xmod + 5 * D;
+      np = 0;
+      if (!last) STK_TRY(tc_problem(e, pc + "mlp.fc2", w.h_c_hi, w.h_c_lo, Mc, erc, &pr[np++]));
+      STK_TRY(tc_problem(e, px + "mlp.fc2", w.h_x_hi, w.h_x_lo, Mx, erx, &pr[np++]));
+      STK_TRY(lintc2(e, pr, np, s));
+      continue;
+    }
     if (!last) {
       STK_TRY(pre_attention(e, pc, w.ctx, Mc, cmod, cmod + D, 6 * D, Kc, w.a_c, w.a_c_hi, w.a_c_lo, Kc, S, 0, s));
     } else {

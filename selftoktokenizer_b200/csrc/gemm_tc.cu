@@ -149,7 +149,7 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
   const bool per_row_gate = MODE == EPI_RESID && e.gate && e.gate_period > 1;
   const bool per_row_add = MODE == EPI_STORE && e.addtab;
   const bool fp16 = e.fp16 != 0;
-  int64_t obase[8];
+  int orow_[8];                                          // output row (32-bit; the 64-bit offset is formed at the access)
   int mrow[8];
   bool rvalid[8];
 #pragma unroll
@@ -158,7 +158,7 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
     rvalid[k] = m < M;
     const int mi = (int)m;
     const int orow = e.rpb_in > 0 ? (mi / e.rpb_in) * e.rpb_out + e.row_off + (mi % e.rpb_in) : mi;
-    obase[k] = (int64_t)orow * e.ldo;
+    orow_[k] = orow;
     mrow[k] = per_row_gate ? mi % e.gate_period : (per_row_add ? mi % e.add_period : 0);
   }
 #pragma unroll 1
@@ -175,7 +175,7 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const bool ok = col_ok && rvalid[k];
-        res[k] = ok ? ldg4(e.resid + obase[k] + n) : zero4;
+        res[k] = ok ? ldg4(e.resid + (int64_t)orow_[k] * e.ldo + n) : zero4;
         gt[k] = (per_row_gate && ok) ? ldg4(e.gate + (int64_t)mrow[k] * e.gate_ld + n) : g0;
       }
     }
@@ -202,7 +202,7 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (!(col_ok && rvalid[k])) continue;
-      const int64_t o = obase[k] + n;
+      const int64_t o = (int64_t)orow_[k] * e.ldo + n;
       if (MODE == EPI_SPLIT) {
         *reinterpret_cast<uint2*>(e.out_hi + o) = make_uint2(pack2(y[k].x, y[k].y, fp16), pack2(y[k].z, y[k].w, fp16));
         if (e.out_lo) {                                  // bf16x3: residual planes
@@ -254,6 +254,10 @@ __device__ __forceinline__ void epilogue_dispatch(const Epilogue& e, uint32_t tm
     else epilogue_block<EPI_STORE, false>(e, tmem_addr, stage, lane, m_base, M, n_first, N);
   }
 }
+
+struct TcMaps {
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+};
 
 struct GemmParams {
   int64_t M;
@@ -464,9 +468,10 @@ __device__ __forceinline__ void pair_coords(int t, int pm_tiles, int n_tiles, in
 
 template <int NSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-                const GemmParams p) {
+gemm_tc2_kernel(const __grid_constant__ TcMaps maps0, const __grid_constant__ TcMaps maps1, const GemmParams p0,
+                const GemmParams p1) {
+  // Up to two independent problems (same NSPLIT / operand type) share the launch: the context- and the image-stream GEMM of
+  // a layer.  Tiles of problem 0 come first; problem 1 may be empty (M == 0).
   using C = Cfg2<NSPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -481,15 +486,21 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int pm_tiles = (int)((p.M + 2 * BM - 1) / (2 * BM)), n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = pm_tiles * n_tiles;
-  const int nk = (p.K + BK - 1) / BK;
+  const int pm_tiles0 = (int)((p0.M + 2 * BM - 1) / (2 * BM)), n_tiles0 = (p0.N + BN - 1) / BN;
+  const int pm_tiles1 = (int)((p1.M + 2 * BM - 1) / (2 * BM)), n_tiles1 = (p1.N + BN - 1) / BN;
+  const int tiles0 = pm_tiles0 * n_tiles0;
+  const int num_tiles = tiles0 + pm_tiles1 * n_tiles1;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a_hi);
-    tma_prefetch_desc(&map_b_hi);
-    if (NSPLIT == 3) { tma_prefetch_desc(&map_a_lo); tma_prefetch_desc(&map_b_lo); }
+    tma_prefetch_desc(&maps0.a_hi);
+    tma_prefetch_desc(&maps0.b_hi);
+    if (NSPLIT == 3) { tma_prefetch_desc(&maps0.a_lo); tma_prefetch_desc(&maps0.b_lo); }
+    if (p1.M > 0) {
+      tma_prefetch_desc(&maps1.a_hi);
+      tma_prefetch_desc(&maps1.b_hi);
+      if (NSPLIT == 3) { tma_prefetch_desc(&maps1.a_lo); tma_prefetch_desc(&maps1.b_lo); }
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -511,8 +522,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const bool second = t >= tiles0;
+        const TcMaps& mp = second ? maps1 : maps0;
         int pm, n_blk;
-        pair_coords(t, pm_tiles, n_tiles, pm, n_blk);
+        if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, pm, n_blk);
+        else pair_coords(t, pm_tiles0, n_tiles0, pm, n_blk);
+        const int nk = ((second ? p1.K : p0.K) + BK - 1) / BK;
         const int m_row = pm * 2 * BM + (int)rank * BM;            // this CTA's 128 A rows
         const int n_row = n_blk * BN + (int)rank * (BN / 2);       // this CTA's half of the W tile
         for (int kb = 0; kb < nk; ++kb) {
@@ -520,11 +535,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t fb = full_bar(stage) & 0xFEFFFFFFu;       // leader's barrier (peer bit cleared)
           if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-          tma_load_2d_2sm(sa, &map_a_hi, fb, kb * BK, m_row);
-          tma_load_2d_2sm(sa + C::PLANES * A_TILE_BYTES, &map_b_hi, fb, kb * BK, n_row);
+          tma_load_2d_2sm(sa, &mp.a_hi, fb, kb * BK, m_row);
+          tma_load_2d_2sm(sa + C::PLANES * A_TILE_BYTES, &mp.b_hi, fb, kb * BK, n_row);
           if (NSPLIT == 3) {
-            tma_load_2d_2sm(sa + A_TILE_BYTES, &map_a_lo, fb, kb * BK, m_row);
-            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + C::HALF_B_BYTES, &map_b_lo, fb, kb * BK, n_row);
+            tma_load_2d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, kb * BK, m_row);
+            tma_load_2d_2sm(sa + 2 * A_TILE_BYTES + C::HALF_B_BYTES, &mp.b_lo, fb, kb * BK, n_row);
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -533,12 +548,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else if (warp == 1) {
     // =========================================================== MMA issuer (leader CTA only)
     if (leader && lane == 0) {
-      const uint32_t idesc = make_idesc(2 * BM, BN, p.fp16);
+      const uint32_t idesc = make_idesc(2 * BM, BN, p0.fp16);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
+        const int nk = ((t >= tiles0 ? p1.K : p0.K) + BK - 1) / BK;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -569,12 +585,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   } else {
     // =========================================================== epilogue warps 2..9 of both CTAs
     const int quarter = warp & 3, half = (warp - 2) >> 2;        // TMEM lane quarter = warp % 4; column half
-    const Epilogue& e = p.ep;
     float* stage = reinterpret_cast<float*>(smem_raw + (bar_base + 256 - smem_u32(smem_raw))) + (warp - 2) * EPI_STAGE_FLOATS;
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const bool second = t >= tiles0;
+      const GemmParams& p = second ? p1 : p0;
+      const Epilogue& e = p.ep;
       int pm, n_blk;
-      pair_coords(t, pm_tiles, n_tiles, pm, n_blk);
+      if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, pm, n_blk);
+      else pair_coords(t, pm_tiles0, n_tiles0, pm, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       epilogue_prefetch(e, lane, (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
@@ -661,52 +680,78 @@ int gemm_tc_init() {
   return 0;
 }
 
-int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* W_hi,
-                   const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
-                   cudaStream_t s, int fp16) {
-  STK_CHECK(g_encode, -3, "gemm_tc_init has not been called");
-  STK_CHECK(A_hi && W_hi && M > 0 && N > 0 && K > 0, -1, "gemm_tc: bad arguments");
-  STK_CHECK(nsplit == 1 || (nsplit == 3 && A_lo && W_lo), -1, "gemm_tc: nsplit must be 1, or 3 with lo planes");
+static int check_problem(const TcProblem& q, int nsplit, int fp16) {
+  const Epilogue& ep = q.ep;
+  STK_CHECK(q.A_hi && q.W_hi && q.M > 0 && q.N > 0 && q.K > 0, -1, "gemm_tc: bad arguments");
+  STK_CHECK(nsplit == 1 || (nsplit == 3 && q.A_lo && q.W_lo), -1, "gemm_tc: nsplit must be 1, or 3 with lo planes");
   STK_CHECK(!fp16 || nsplit == 1, -1, "gemm_tc: the fp16 mode is single-pass");
   STK_CHECK(ep.act == ACT_NONE || (ep.act == ACT_GELU && ep.mode != EPI_RESID), -2,
             "gemm_tc: epilogue activation must be none, or GELU-tanh with the store / split modes");
   STK_CHECK(ep.mode != EPI_STORE || ep.addtab == nullptr || ep.add_ld % 4 == 0, -2, "gemm_tc: addtab pitch must be a multiple of 4");
-  STK_CHECK(K % 8 == 0, -2, "gemm_tc: K must be a multiple of 8 (16-byte TMA row pitch)");
-  STK_CHECK(ep.ldo % 4 == 0 && N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");
+  STK_CHECK(q.K % 8 == 0, -2, "gemm_tc: K must be a multiple of 8 (16-byte TMA row pitch)");
+  STK_CHECK(ep.ldo % 4 == 0 && q.N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");
   STK_CHECK(ep.mode != EPI_RESID || ep.gate == nullptr || ep.gate_ld % 4 == 0, -2, "gemm_tc: gate pitch must be a multiple of 4");
-  CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-  const bool pair = g_gemm_ctas == 2 && g_num_sms >= 2;
-  const int b_box = pair ? BN / 2 : BN;
-  STK_TRY(make_map(&ma_hi, A_hi, M, K, BM, fp16));
-  STK_TRY(make_map(&mb_hi, W_hi, N, K, b_box, fp16));
+  return 0;
+}
+
+static int make_maps(TcMaps* m, const TcProblem& q, int nsplit, int fp16, int b_box) {
+  STK_TRY(make_map(&m->a_hi, q.A_hi, q.M, q.K, BM, fp16));
+  STK_TRY(make_map(&m->b_hi, q.W_hi, q.N, q.K, b_box, fp16));
   if (nsplit == 3) {
-    STK_TRY(make_map(&ma_lo, A_lo, M, K, BM, fp16));
-    STK_TRY(make_map(&mb_lo, W_lo, N, K, b_box, fp16));
+    STK_TRY(make_map(&m->a_lo, q.A_lo, q.M, q.K, BM, fp16));
+    STK_TRY(make_map(&m->b_lo, q.W_lo, q.N, q.K, b_box, fp16));
   } else {
-    ma_lo = ma_hi; mb_lo = mb_hi;
+    m->a_lo = m->a_hi; m->b_lo = m->b_hi;
   }
-  GemmParams p{M, N, K, fp16, ep};
-  const int m_tiles = (int)((M + BM - 1) / BM), n_tiles = (N + BN - 1) / BN;
-  if (pair) {
-    const int pairs = (int)((M + 2 * BM - 1) / (2 * BM)) * n_tiles;
-    const int clusters = pairs < g_num_sms / 2 ? pairs : g_num_sms / 2;
-    if (nsplit == 3)
-      gemm_tc2_kernel<3><<<2 * clusters, NUM_THREADS, Cfg2<3>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-    else
-      gemm_tc2_kernel<1><<<2 * clusters, NUM_THREADS, Cfg2<1>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-    count_launch();
-    STK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// One launch for up to two independent problems (the context- and the image-stream GEMM of an MMDiT layer): their tiles share
+// the persistent grid, so the small N = 1536 GEMMs no longer pay a partially filled last wave each.
+int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream_t s, int fp16) {
+  STK_CHECK(g_encode, -3, "gemm_tc_init has not been called");
+  STK_CHECK(probs && (n == 1 || n == 2), -1, "gemm_tc: one or two problems per launch");
+  for (int i = 0; i < n; ++i) STK_TRY(check_problem(probs[i], nsplit, fp16));
+  const bool pair = g_gemm_ctas == 2 && g_num_sms >= 2;
+  if (!pair) {                                            // single-CTA bisecting kernel: one launch per problem
+    for (int i = 0; i < n; ++i) {
+      const TcProblem& q = probs[i];
+      TcMaps m;
+      STK_TRY(make_maps(&m, q, nsplit, fp16, BN));
+      GemmParams p{q.M, q.N, q.K, fp16, q.ep};
+      const int tiles = (int)((q.M + BM - 1) / BM) * ((q.N + BN - 1) / BN);
+      const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+      if (nsplit == 3) gemm_tc_kernel<3><<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, s>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, p);
+      else gemm_tc_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, s>>>(m.a_hi, m.a_lo, m.b_hi, m.b_lo, p);
+      count_launch();
+      STK_CUDA(cudaGetLastError());
+    }
     return 0;
   }
-  const int tiles = m_tiles * n_tiles;
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  if (nsplit == 3)
-    gemm_tc_kernel<3><<<grid, NUM_THREADS, Cfg<3>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
-  else
-    gemm_tc_kernel<1><<<grid, NUM_THREADS, Cfg<1>::SMEM_BYTES, s>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+  TcMaps m0, m1;
+  STK_TRY(make_maps(&m0, probs[0], nsplit, fp16, BN / 2));
+  GemmParams p0{probs[0].M, probs[0].N, probs[0].K, fp16, probs[0].ep};
+  GemmParams p1{0, probs[0].N, probs[0].K, fp16, probs[0].ep};
+  m1 = m0;
+  int pairs = (int)((probs[0].M + 2 * BM - 1) / (2 * BM)) * ((probs[0].N + BN - 1) / BN);
+  if (n == 2) {
+    STK_TRY(make_maps(&m1, probs[1], nsplit, fp16, BN / 2));
+    p1 = GemmParams{probs[1].M, probs[1].N, probs[1].K, fp16, probs[1].ep};
+    pairs += (int)((probs[1].M + 2 * BM - 1) / (2 * BM)) * ((probs[1].N + BN - 1) / BN);
+  }
+  const int clusters = pairs < g_num_sms / 2 ? pairs : g_num_sms / 2;
+  if (nsplit == 3) gemm_tc2_kernel<3><<<2 * clusters, NUM_THREADS, Cfg2<3>::SMEM_BYTES, s>>>(m0, m1, p0, p1);
+  else gemm_tc2_kernel<1><<<2 * clusters, NUM_THREADS, Cfg2<1>::SMEM_BYTES, s>>>(m0, m1, p0, p1);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* W_hi,
+                   const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
+                   cudaStream_t s, int fp16) {
+  TcProblem q{A_hi, A_lo, W_hi, W_lo, M, N, K, ep};
+  return launch_gemm_tc_grouped(&q, 1, nsplit, s, fp16);
 }
 
 }  // namespace stk

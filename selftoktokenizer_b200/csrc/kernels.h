@@ -79,6 +79,13 @@ int launch_copy_rows(const float* src, int64_t src_bs, float* dst, int64_t dst_b
 int launch_gemm_tc(const __nv_bfloat16* A_hi, const __nv_bfloat16* A_lo, const __nv_bfloat16* W_hi,
                    const __nv_bfloat16* W_lo, int64_t M, int N, int K, int nsplit, const Epilogue& ep,
                    cudaStream_t s, int fp16 = 0);
+struct TcProblem {
+  const __nv_bfloat16* A_hi; const __nv_bfloat16* A_lo; const __nv_bfloat16* W_hi; const __nv_bfloat16* W_lo;
+  int64_t M; int N; int K;
+  Epilogue ep;
+};
+// one launch for one or two independent problems of the same operand type (cta_group::2 kernel)
+int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream_t s, int fp16 = 0);
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes; idempotent
 void gemm_tc_set_ctas(int n);   // 2 (default): cta_group::2 pair kernel; 1: single-CTA kernel
 

@@ -125,6 +125,38 @@ def test_pipeline_api_latent_boundary(tiny_sd, gold):
         pipe.decoding(idx, DEV)                                        # pixel API needs the SD3 VAE
 
 
+# A second reduced geometry with deliberately ragged sizes (K = 40 tokens, 6x6 = 36 image tokens, S = 41..76, rows not multiples of
+# any tile): no reference fixture, so the checker is the (pinned) oracle run on the CPU in the same test.
+RAGGED = dataclasses.replace(C.TINY, K=40, k_per_stage=(14, 10, 8, 5, 3), latent=12, enc_pos_max=24, dit_pos_max=10, enc_depth=1,
+                             dit_depth=2, codebook_size=2048)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16"])
+def test_ragged_geometry_against_oracle(precision):
+    from selftoktokenizer_b200.capi import Engine
+    d = RAGGED
+    d.validate()
+    sd = synth.synth_state_dict(d, seed=3)
+    x0 = synth.synth_tensor("ragged.x0", (5, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    noise = synth.synth_tensor("ragged.noise", (5, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    outs_q_ref, tok_ref, z_ref = O.encode(sd, d, x0)
+    x_ref = O.decode(sd, d, tok_ref, noise, steps=50)
+    eng = Engine(d, sd, device=DEV, precision=precision)
+    tok, outs_q, feats = eng.encode(x0, return_aux=True)
+    assert (feats.cpu() - z_ref).abs().max() < 1e-4
+    # margins of the oracle's own argmax decide whether a mismatch is a tie
+    zn = torch.nn.functional.normalize(torch.nn.functional.linear(z_ref, sd["encoder.quantizer.project_in.weight"],
+                                                                  sd["encoder.quantizer.project_in.bias"]), dim=-1)
+    top2 = (zn.reshape(-1, 16) @ sd["encoder.quantizer._codebook.embed"][0].t()).topk(2, dim=-1).values
+    margin = (top2[:, 0] - top2[:, 1]).reshape(tok_ref.shape).numpy()
+    _check_tokens(tok.cpu().numpy(), tok_ref.numpy(), margin, "ragged encode")
+    x = eng.decode(tok_ref, noise).cpu()
+    err = float((x - x_ref).abs().max())
+    print(f"[{precision}] ragged geometry 50-step decode: max-abs err vs oracle {err:.3e}")
+    assert err < TOL[precision]
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------ full geometry
 @pytest.fixture(scope="module")
 def full_sd():
