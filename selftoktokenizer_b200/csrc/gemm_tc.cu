@@ -183,15 +183,21 @@ __device__ __forceinline__ void epilogue_block(const Epilogue& e, uint32_t tmem_
     tmem_ld32(tmem_addr + (uint32_t)(c * 32), r);
     tmem_ld_wait();
     __syncwarp();                                       // previous chunk fully read back
+#ifndef STK_EXPERIMENT_NO_STAGING
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       *reinterpret_cast<uint4*>(&stage[lane * 32 + ((q ^ (lane & 7)) << 2)]) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
     __syncwarp();
+#endif
     float4 y[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int row = 4 * k + rsub;
+#ifndef STK_EXPERIMENT_NO_STAGING
       const float4 v = *reinterpret_cast<const float4*>(&stage[row * 32 + ((cq ^ (row & 7)) << 2)]);
+#else       // timing experiment only (wrong values): how much of the epilogue cost is the shared-memory transpose?
+      const float4 v = make_float4(__uint_as_float(r[4 * k]), __uint_as_float(r[4 * k + 1]), __uint_as_float(r[4 * k + 2]), __uint_as_float(r[4 * k + 3]));
+#endif
       y[k] = make_float4(v.x + bias.x, v.y + bias.y, v.z + bias.z, v.w + bias.w);
       if (GELU) y[k] = gelu_tanh_fast4(y[k]);
       if (MODE == EPI_RESID) {
@@ -589,18 +595,27 @@ gemm_tc2_kernel(const __grid_constant__ TcMaps maps0, const __grid_constant__ Tc
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const bool second = t >= tiles0;
-      const GemmParams& p = second ? p1 : p0;
-      const Epilogue& e = p.ep;
       int pm, n_blk;
       if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, pm, n_blk);
       else pair_coords(t, pm_tiles0, n_tiles0, pm, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      epilogue_prefetch(e, lane, (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      epilogue_dispatch(e, tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)), stage, lane,
-                     (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32, p.M, n_blk * BN + half * (BN / 2), p.N);
+      const int64_t m_base = (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32;
+      const int n_first = n_blk * BN + half * (BN / 2);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+      // the two problems are handled by separate (statically addressed) copies of the epilogue: selecting the parameter block
+      // dynamically costs registers in the hottest loop of the kernel
+      if (!second) {
+        epilogue_prefetch(p0.ep, lane, m_base, p0.M, n_first, p0.N);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        epilogue_dispatch(p0.ep, taddr, stage, lane, m_base, p0.M, n_first, p0.N);
+      } else {
+        epilogue_prefetch(p1.ep, lane, m_base, p1.M, n_first, p1.N);
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        epilogue_dispatch(p1.ep, taddr, stage, lane, m_base, p1.M, n_first, p1.N);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);       // the leader's barrier counts all 8 epilogue warps
