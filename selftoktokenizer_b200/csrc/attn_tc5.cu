@@ -1,15 +1,15 @@
 // Joint attention of the MMDiT on tcgen05 tensor cores with TMEM accumulators (sm_100a), head_dim 64, single-pass
 // 16-bit operands (IEEE half or bf16), fp32 softmax.
 //
-//   CTA            128 query rows of one (image, head); grid (ceil(S/128), H, B); 2 CTAs co-reside per SM (80 KiB smem,
+//   CTA            128 query rows of one (image, head); grid (ceil(S/128), H, B); 2 CTAs co-reside per SM (68 KiB smem,
 //                  256 TMEM columns each); S is double-buffered in TMEM so Q K^T of tile j+1 overlaps the softmax of tile j
 //   warp 0         TMA producer: Q tile once, then K and V tiles (64 keys x 64 dims) through a 3-stage ring
 //   warp 1         MMA issuer (one thread):  S = Q K^T  -> TMEM cols [0,64) / [64,128) (UMMA 128x64x16 x4, both operands K-major)
-//                                            O += P V   -> TMEM cols [128,192)      (UMMA 128x64x16 x4, A = P K-major from smem,
-//                                                                              B = V MN-major straight from the TMA tile)
+//                                            O += P V   -> TMEM cols [128,192)      (UMMA 128x64x16 x4, A = P from TMEM cols
+//                                                                              [192,256), B = V MN-major straight from the TMA tile)
 //   warps 2-9      two threads per query row (TMEM lane quarter = warp % 4, 32 of the 64 keys / dims each): tcgen05.ld the
 //                  half row of S, online softmax in registers (row max exchanged through smem, no shuffles), rescale the
-//                  half row of O in TMEM (tcgen05.ld / tcgen05.st), write P as 16-bit into the SWIZZLE_128B A-operand tile,
+//                  half row of O in TMEM (tcgen05.ld / tcgen05.st), tcgen05.st P as packed 16-bit pairs (A operand in TMEM),
 //                  finally normalise O and store it as the A-operand planes of the proj GEMM
 //
 // Same contract as attn_tc.cu (sd3/mmdit.py:521-531, sd3/other_impls.py:37-45): dense non-causal attention over the joint
@@ -19,6 +19,8 @@
 
 #include <cuda.h>
 
+#include <algorithm>
+
 namespace stk {
 
 // provided by gemm_tc.cu
@@ -27,13 +29,14 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 namespace {
 
-constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 3;
+constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 4;
 constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2, P_BYTES = BQ * BKV * 2;
-constexpr int SMEM_TILES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + 2 * P_BYTES;  // 16 + 48 + 2 x 16 = 96 KiB (P double-buffered)
+constexpr int SMEM_TILES = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES;            // 2 x 16 + 64 = 96 KiB (P lives in TMEM)
 constexpr int XCH_BYTES = 6 * BQ * 4;               // row-max exchange (2 parities x 2 halves) + partial-sum exchange (2 halves)
-constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 128 + XCH_BYTES;
-constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O [128,192)
+constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 160 + XCH_BYTES;   // tiles + alignment slack + barriers + exchange
+constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O0 [128,192) | O1 [192,256); P_g overwrites half of S_g in place
 constexpr int NUM_THREADS = 64 + 8 * 32;        // TMA warp, MMA warp, 8 softmax warps
+constexpr float kRescaleThreshold = 8.0f;       // log2 units
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -83,6 +86,14 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (P of the P V product), B from shared memory
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -103,6 +114,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
         "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
         "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -131,6 +150,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pipe: (x0, x1) = (s0, s1) * scale + nsub;  (a0, a1) += (e0, e1)
+__device__ __forceinline__ void scale_sub2(uint32_t s0, uint32_t s1, float scale, float nsub, float& x0, float& x1) {
+  asm("{\n\t.reg .b64 x, sc, sb;\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 sc, {%4, %4};\n\t"
+      "mov.b64 sb, {%5, %5};\n\t"
+      "fma.rn.f32x2 x, x, sc, sb;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t}"
+      : "=f"(x0), "=f"(x1) : "r"(s0), "r"(s1), "f"(scale), "f"(nsub));
+}
+__device__ __forceinline__ void add2(float& a0, float& a1, float e0, float e1) {
+  asm("{\n\t.reg .b64 a, b;\n\t"
+      "mov.b64 a, {%0, %1};\n\t"
+      "mov.b64 b, {%2, %3};\n\t"
+      "add.f32x2 a, a, b;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "+f"(a0), "+f"(a1) : "f"(e0), "f"(e1));
+}
 // two fp32 -> packed 16-bit pair (IEEE half or bf16), one cvt instruction
 __device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
   uint32_t r;
@@ -141,7 +178,7 @@ __device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
 
 struct Attn5Params {
   AttnOut out;
-  int S, H, ctx_rows, ctx_keys, fp16;
+  int B, S, H, ctx_rows, ctx_keys, fp16;
   float scale_log2e;
 };
 
@@ -150,31 +187,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_s = base;
-  const uint32_t kv_s = base + Q_BYTES;                       // stage st: K at kv_s + st*2*KV_TILE_BYTES, V right after
-  const uint32_t p_s = kv_s + KV_STAGES * 2 * KV_TILE_BYTES;
-  const uint32_t bars = p_s + 2 * P_BYTES;
+  const uint32_t q_s = base;                                  // Q buffer qb at q_s + qb * Q_BYTES
+  const uint32_t kv_s = base + 2 * Q_BYTES;                   // stage st: K at kv_s + st*2*KV_TILE_BYTES, V right after
+  const uint32_t bars = kv_s + KV_STAGES * 2 * KV_TILE_BYTES;
   // every per-tile barrier exists twice (tile parity) so that no waiter can be lapped by two phases
-  const uint32_t q_full = bars;
-  auto p_ready = [&](int pb) { return bars + 8 + 8u * pb; };
-  auto pv_done = [&](int pb) { return bars + 24 + 8u * pb; };
-  auto s_full = [&](int sb) { return bars + 40 + 8u * sb; };
-  auto kv_full = [&](int st) { return bars + 56 + 8u * st; };
-  auto kv_empty = [&](int st) { return bars + 80 + 8u * st; };
-  const uint32_t tmem_slot = bars + 104;
-  const uint32_t xch_s = bars + 128;
+  auto q_full = [&](int qb) { return bars + 8u * qb; };
+  auto q_empty = [&](int qb) { return bars + 16 + 8u * qb; };
+  auto p_ready = [&](int pb) { return bars + 32 + 8u * pb; };
+  auto pv_done = [&](int pb) { return bars + 48 + 8u * pb; };
+  auto s_full = [&](int sb) { return bars + 64 + 8u * sb; };
+  auto kv_full = [&](int st) { return bars + 80 + 8u * st; };
+  auto kv_empty = [&](int st) { return bars + 80 + 8u * KV_STAGES + 8u * st; };
+  const uint32_t tmem_slot = bars + 80 + 16u * KV_STAGES;
+  const uint32_t xch_s = tmem_slot + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  uint8_t* p_ptr = smem_raw + (p_s - smem_u32(smem_raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const int S = p.S;
-  const int kmax_cta = (q0 + BQ <= p.ctx_rows) ? p.ctx_keys : S;          // every row of this CTA is a context row
-  const int n_tiles = (kmax_cta + BKV - 1) / BKV;
+  // persistent CTA: work items (image b, head h, query tile qt), qt fastest, so that the CTAs running side by side share
+  // the K / V tiles of one (b, h) in L2.  All roles walk the same item sequence with a CTA-global tile counter g that
+  // drives the ring stages and barrier parities, so the TMA / MMA warps run ahead into the next item while the softmax
+  // warps finish the current one (no per-item prologue bubble).
+  const int nq = (S + BQ - 1) / BQ;
+  const int n_items = nq * p.H * p.B;
+  auto item_tiles = [&](int qt) {
+    const int kmax_cta = ((qt + 1) * BQ <= p.ctx_rows) ? p.ctx_keys : S;  // every row of the tile is a context row
+    return (kmax_cta + BKV - 1) / BKV;
+  };
 
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1); mbar_init(s_full(0), 1); mbar_init(s_full(1), 1);
-    mbar_init(p_ready(0), 8); mbar_init(p_ready(1), 8); mbar_init(pv_done(0), 1); mbar_init(pv_done(1), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), 8); mbar_init(pv_done(i), 1);
+    }
     for (int st = 0; st < KV_STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -186,22 +230,37 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const uint32_t s_tmem0 = tmem_base, o_tmem = tmem_base + 128;       // S buffer sb at s_tmem0 + 64 * sb
+  // S buffer sb at s_tmem0 + 64 * sb; O buffer (item parity) ob at o_tmem0 + 64 * ob.  P_g (16-bit pairs, two keys per
+  // column) replaces S_g in place: the thread that loaded S columns [32 half, 32 half + 32) writes its 32 keys into columns
+  // [32 half, 32 half + 16) -- nobody else reads those, and Q K^T of tile g+2 (same buffer) is issued after P V of tile g.
+  const uint32_t s_tmem0 = tmem_base, o_tmem0 = tmem_base + 128;
 
   if (warp == 0) {
     // =========================================================== TMA producer
     if (lane == 0) {
-      const int row0 = b * S;                                           // first row of this image in the [B*S, 3*H*64] matrix
-      mbar_expect_tx(q_full, Q_BYTES);
-      tma_load_2d(q_s, &map_q, q_full, h * HD, row0 + q0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(kv_empty(st), ph ^ 1);
-        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
-        mbar_expect_tx(kv_full(st), 2 * KV_TILE_BYTES);
-        tma_load_2d(ks, &map_kv, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
-        tma_load_2d(ks + KV_TILE_BYTES, &map_kv, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+      auto load_q = [&](int item, int n) {                              // n = CTA-local item number
+        const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+        const int qb = n & 1;
+        mbar_wait(q_empty(qb), ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(q_full(qb), Q_BYTES);
+        tma_load_2d(q_s + qb * Q_BYTES, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
+      };
+      int g = 0, n = 0;
+      if ((int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+        const int row0 = b * S;                                         // first row of this image in the [B*S, 3*H*64] matrix
+        const int n_tiles = item_tiles(qt);
+        if (item + (int)gridDim.x < n_items) load_q(item + gridDim.x, n + 1);   // next item's Q, one item ahead
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          const int st = g % KV_STAGES;
+          const uint32_t ph = (g / KV_STAGES) & 1;
+          mbar_wait(kv_empty(st), ph ^ 1);
+          const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
+          mbar_expect_tx(kv_full(st), 2 * KV_TILE_BYTES);
+          tma_load_2d(ks, &map_kv, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
+          tma_load_2d(ks + KV_TILE_BYTES, &map_kv, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+        }
       }
     }
   } else if (warp == 1) {
@@ -209,30 +268,42 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc(BQ, BKV, FP16 ? 1 : 0, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
       const uint32_t idesc_pv = make_idesc(BQ, HD, FP16 ? 1 : 0, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
-      mbar_wait(q_full, 0);
-      auto issue_qk = [&](int j) {                                       // S[j & 1] = Q K_j^T
-        const int st = j % KV_STAGES;
-        mbar_wait(kv_full(st), (j / KV_STAGES) & 1);
+      // S[gg & 1] = Q_n K_gg^T for the tile with CTA-global index gg of local item n; `last` releases the Q buffer
+      auto issue_qk = [&](int n, int gg, bool first, bool last) {
+        const int qb = n & 1, st = gg % KV_STAGES;
+        if (first) mbar_wait(q_full(qb), (n >> 1) & 1);
+        mbar_wait(kv_full(st), (gg / KV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
+        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES, qs = q_s + qb * Q_BYTES;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)                                // K dimension = head dim: 32 B per k-step inside the row
-          tc_mma_f16(s_tmem0 + 64 * (j & 1), make_smem_desc(q_s + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-        tc_commit(s_full(j & 1));
+          tc_mma_f16(s_tmem0 + 64 * (gg & 1), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        tc_commit(s_full(gg & 1));
+        if (last) tc_commit(q_empty(qb));
       };
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        if (j + 1 < n_tiles) issue_qk(j + 1);                            // overlaps the softmax of tile j (S is double-buffered)
-        const int st = j % KV_STAGES;
-        const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
-        mbar_wait(p_ready(j & 1), (j >> 1) & 1);                         // P_j in smem, O rescaled, S[j & 1] consumed
-        tc_fence_after();
+      int g = 0, n = 0;
+      if ((int)blockIdx.x < n_items) {
+        const int nt0 = item_tiles((int)blockIdx.x % nq);
+        issue_qk(0, 0, true, nt0 == 1);
+      }
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+        const int n_tiles = item_tiles(item % nq);
+        const int next = item + gridDim.x;
+        for (int j = 0; j < n_tiles; ++j, ++g) {
+          // look-ahead Q K^T (overlaps the softmax of tile g: S is double-buffered); crosses into the next item at the end
+          if (j + 1 < n_tiles) issue_qk(n, g + 1, false, j + 2 == n_tiles);
+          else if (next < n_items) issue_qk(n + 1, g + 1, true, item_tiles(next % nq) == 1);
+          const int st = g % KV_STAGES;
+          const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
+          mbar_wait(p_ready(g & 1), (g >> 1) & 1);                       // P_g in TMEM, O rescaled (or read out), S[g & 1] consumed
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)                               // K dimension = keys: 16 keys = 2 atoms of 8 key rows
-          tc_mma_f16(o_tmem, make_smem_desc(p_s + (j & 1) * P_BYTES + k * 32), make_smem_desc(vs + k * 2048), idesc_pv,
-                     (j > 0 || k > 0) ? 1u : 0u);
-        tc_commit(kv_empty(st));                                         // K/V stage reusable once QK_j and PV_j retire
-        tc_commit(pv_done(j & 1));                                       // P[j & 1] free again; O holds tiles 0..j
+          for (int k = 0; k < BKV / 16; ++k)                             // K dimension = keys: 16 keys = 2 atoms of 8 key rows
+            tc_mma_f16_ts(o_tmem0 + 64 * (n & 1), s_tmem0 + 64 * (g & 1) + 32 * (k >> 1) + 8 * (k & 1), make_smem_desc(vs + k * 2048),
+                          idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          tc_commit(kv_empty(st));                                       // K/V stage reusable once QK_g and PV_g retire
+          tc_commit(pv_done(g & 1));                                     // O[n & 1] holds tiles 0..j of the item
+        }
       }
     }
   } else {
@@ -243,111 +314,135 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // thread-per-row version hide the fixed-latency stalls of the exp / convert chain.
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int rl = quarter * 32 + lane;                                  // row inside the tile = TMEM lane
-    const int row = q0 + rl;
-    const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     float* xch = reinterpret_cast<float*>(smem_raw + (xch_s - smem_u32(smem_raw)));   // [2 halves][128 rows]
-    float m_run = -INFINITY, l_part = 0.f;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(s_full(j & 1), (j >> 1) & 1);
+    // Item epilogue (O / l -> 16-bit planes of the proj GEMM and / or fp32), deferred until after the first tile of the
+    // NEXT item so that its wait on the last P V is already satisfied and the tensor core keeps running: O is
+    // double-buffered by item parity, and the P V that overwrites O[n & 1] (first tile of item n + 2) waits for a p_ready
+    // that every softmax warp arrives at only after this read.
+    auto epilogue = [&](int item, int n, int g_last, float l_run) {
+      const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
+      const int row = qt * BQ + rl;
+      mbar_wait(pv_done(g_last & 1), (g_last >> 1) & 1);
       tc_fence_after();
       uint32_t r0[32];
-      tmem_ld32(s_tmem0 + 64 * (j & 1) + 32 * half + lane_addr, r0);
+      tmem_ld32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
       tmem_ld_wait();
-      const int k0 = j * BKV + 32 * half;
-      if (k0 + 32 > kmax) {                                               // tile straddles this row's key limit
+      if (row < S) {
+        const float inv = 1.0f / l_run;
+        const AttnOut& t = p.out;
+        const bool inA = row < t.split;
+        const int64_t orow = inA ? ((int64_t)b * t.split + row) : ((int64_t)b * (S - t.split) + (row - t.split));
+        float* of = inA ? t.f32_a : t.f32_b;
+        uint16_t* oh = reinterpret_cast<uint16_t*>(inA ? t.hi_a : t.hi_b);
+        uint16_t* ol = reinterpret_cast<uint16_t*>(inA ? t.lo_a : t.lo_b);
+        const int64_t o = orow * t.ld + (int64_t)h * HD + 32 * half;
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (k0 + i >= kmax) r0[i] = 0xff800000u;                        // -inf
+        for (int c = 0; c < 4; ++c) {
+          float y[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) y[q] = __uint_as_float(r0[c * 8 + q]) * inv;
+          if (of) {
+            *reinterpret_cast<float4*>(of + o + c * 8) = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(of + o + c * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          }
+          if (oh) {
+            uint16_t hh[8], ll[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split16(y[q], t.fp16 != 0, hh[q], ll[q]);
+            *reinterpret_cast<uint4*>(oh + o + c * 8) = make_uint4(hh[0] | ((uint32_t)hh[1] << 16), hh[2] | ((uint32_t)hh[3] << 16),
+                                                                   hh[4] | ((uint32_t)hh[5] << 16), hh[6] | ((uint32_t)hh[7] << 16));
+            if (ol) *reinterpret_cast<uint4*>(ol + o + c * 8) = make_uint4(ll[0] | ((uint32_t)ll[1] << 16), ll[2] | ((uint32_t)ll[3] << 16),
+                                                                           ll[4] | ((uint32_t)ll[5] << 16), ll[6] | ((uint32_t)ll[7] << 16));
+          }
+        }
       }
-      float mx;
-      {
-        float mp[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
-#pragma unroll
-        for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
-        mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
-      }
-      // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
-      xch[((j & 1) * 2 + half) * BQ + rl] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      mx = fmaxf(mx, xch[((j & 1) * 2 + (half ^ 1)) * BQ + rl]);
-      const float m_new = fmaxf(m_run, mx * p.scale_log2e);
-      const float sub = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = (m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-      uint32_t w[16];
-      float rsp[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float e0 = ex2_approx(fmaf(__uint_as_float(r0[2 * q]), p.scale_log2e, -sub));
-        const float e1 = ex2_approx(fmaf(__uint_as_float(r0[2 * q + 1]), p.scale_log2e, -sub));
-        rsp[q & 3] += e0 + e1;
-        w[q] = pack2_16(e0, e1, FP16);
-      }
-      const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
-      if (j > 1) mbar_wait(pv_done(j & 1), ((j - 2) >> 1) & 1);          // PV_{j-2} retired: P[j & 1] is free
-      // this thread's 32 keys = 16-byte chunks 4*half .. 4*half+3 of row rl in the SWIZZLE_128B K-major A tile
-      uint8_t* prow = p_ptr + (j & 1) * P_BYTES + rl * 128;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<uint4*>(prow + (((4 * half + c) ^ (rl & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
-      l_part = l_part * corr + rs;
-      m_run = m_new;
-      // rescale this thread's 32 output dims only when some row of the warp moved its maximum
-      if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
-        mbar_wait(pv_done((j - 1) & 1), ((j - 1) >> 1) & 1);              // PV_{j-1} retired: O is stable
+    };
+    int g = 0, n = 0, pend_item = -1, pend_g = 0;
+    float pend_l = 1.f;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      const int qt = item % nq;
+      const int n_tiles = item_tiles(qt);
+      const int row = qt * BQ + rl;
+      const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
+      float m_run = -INFINITY, l_part = 0.f;
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        mbar_wait(s_full(g & 1), (g >> 1) & 1);
         tc_fence_after();
-        tmem_ld32(o_tmem + 32 * half + lane_addr, r0);
+        uint32_t r0[32];
+        tmem_ld32(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, r0);
         tmem_ld_wait();
+        const int k0 = j * BKV + 32 * half;
+        if (k0 + 32 > kmax) {                                             // tile straddles this row's key limit
 #pragma unroll
-        for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
-        tmem_st32(o_tmem + 32 * half + lane_addr, r0);
-        tmem_st_wait();
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // st.shared of P -> visible to the tensor core
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready(j & 1));
-    }
-    // ---- epilogue: combine the partial row sums, O / l -> 16-bit planes (A operand of the proj GEMM) and / or fp32
-    xch[(4 + half) * BQ + rl] = l_part;
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-    const float l_run = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
-    mbar_wait(pv_done((n_tiles - 1) & 1), ((n_tiles - 1) >> 1) & 1);
-    tc_fence_after();
-    uint32_t r0[32];
-    tmem_ld32(o_tmem + 32 * half + lane_addr, r0);
-    tmem_ld_wait();
-    if (row < S) {
-      const float inv = 1.0f / l_run;
-      const AttnOut& t = p.out;
-      const bool inA = row < t.split;
-      const int64_t orow = inA ? ((int64_t)b * t.split + row) : ((int64_t)b * (S - t.split) + (row - t.split));
-      float* of = inA ? t.f32_a : t.f32_b;
-      uint16_t* oh = reinterpret_cast<uint16_t*>(inA ? t.hi_a : t.hi_b);
-      uint16_t* ol = reinterpret_cast<uint16_t*>(inA ? t.lo_a : t.lo_b);
-      const int64_t o = orow * t.ld + (int64_t)h * HD + 32 * half;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float y[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) y[q] = __uint_as_float(r0[c * 8 + q]) * inv;
-        if (of) {
-          *reinterpret_cast<float4*>(of + o + c * 8) = make_float4(y[0], y[1], y[2], y[3]);
-          *reinterpret_cast<float4*>(of + o + c * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
+          for (int i = 0; i < 32; ++i)
+            if (k0 + i >= kmax) r0[i] = 0xff800000u;                      // -inf
         }
-        if (oh) {
-          uint16_t hh[8], ll[8];
+        float mx;
+        {
+          float mp[4];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) split16(y[q], t.fp16 != 0, hh[q], ll[q]);
-          *reinterpret_cast<uint4*>(oh + o + c * 8) = make_uint4(hh[0] | ((uint32_t)hh[1] << 16), hh[2] | ((uint32_t)hh[3] << 16),
-                                                                 hh[4] | ((uint32_t)hh[5] << 16), hh[6] | ((uint32_t)hh[7] << 16));
-          if (ol) *reinterpret_cast<uint4*>(ol + o + c * 8) = make_uint4(ll[0] | ((uint32_t)ll[1] << 16), ll[2] | ((uint32_t)ll[3] << 16),
-                                                                         ll[4] | ((uint32_t)ll[5] << 16), ll[6] | ((uint32_t)ll[7] << 16));
+          for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
+#pragma unroll
+          for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
+          mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+        }
+        // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
+        xch[((g & 1) * 2 + half) * BQ + rl] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        mx = fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
+        // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays
+        // exact enough in 16 bits and the final O / l normalisation cancels the stale offset), so the O correction pass and
+        // its wait on the previous P V are rare instead of per tile.  (-inf - -inf = NaN keeps m_run: comparison is false.)
+        float m_new = fmaxf(m_run, mx * p.scale_log2e);
+        if (m_new - m_run <= kRescaleThreshold) m_new = m_run;
+        const float sub = (m_new == -INFINITY) ? 0.f : m_new;
+        const float corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
+        // scale / subtract and the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2): the softmax warps are
+        // co-limited by issue slots and the MUFU pipe, so every instruction saved around the 32 ex2 counts
+        uint32_t w[16];
+        float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+        const float nsub = -sub;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float x0, x1;
+          scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
+          const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+          add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
+          w[q] = pack2_16(e0, e1, FP16);
+        }
+        const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
+        // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
+        tmem_st16(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, w);
+        l_part = l_part * corr + rs;
+        m_run = m_new;
+        // rescale this thread's 32 output dims only when some row of the warp moved its maximum
+        if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
+          mbar_wait(pv_done((g - 1) & 1), ((g - 1) >> 1) & 1);            // PV of the previous tile retired: O is stable
+          tc_fence_after();
+          tmem_ld32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
+          tmem_st32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+        }
+        tmem_st_wait();                                                   // P (and the rescaled O) are in TMEM
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready(g & 1));
+        if (j == 0 && pend_item >= 0) {
+          epilogue(pend_item, n - 1, pend_g, pend_l);
+          pend_item = -1;
         }
       }
+      // ---- item end: combine the partial row sums now, leave the read-out of O for after the next item's first tile
+      xch[(4 + half) * BQ + rl] = l_part;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      pend_l = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
+      pend_item = item;
+      pend_g = g - 1;
     }
+    if (pend_item >= 0) epilogue(pend_item, n - 1, pend_g, pend_l);
   }
   tc_fence_before();
   __syncthreads();
@@ -358,6 +453,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 }
 
 bool g_attr_set = false;
+int g_num_sms = 148;
 
 }  // namespace
 
@@ -367,6 +463,9 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
   STK_TRY(gemm_tc_init());
   if (!g_attr_set) {
+    int dev = 0;
+    STK_CUDA(cudaGetDevice(&dev));
+    STK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_set = true;
@@ -375,8 +474,9 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)3 * H * HD;
   STK_TRY(make_tensor_map_2d(&mq, qkv16, rows, cols, BQ, HD, fp16));
   STK_TRY(make_tensor_map_2d(&mkv, qkv16, rows, cols, BKV, HD, fp16));
-  Attn5Params p{out, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
-  dim3 grid((S + BQ - 1) / BQ, H, B);
+  Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
+  const int n_items = ((S + BQ - 1) / BQ) * H * B;
+  dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
   if (fp16) attention_tc5_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   else attention_tc5_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   count_launch();
