@@ -160,30 +160,48 @@ int launch_linear_f32(const float* A, int64_t lda, const float* W, int64_t ldw, 
 // One warp per row.  mean and biased variance in two register-resident passes (matches F.layer_norm semantics),
 // out = xn * (1 + scale[m % period]) + shift[m % period].
 // Per-position tables (period > 1, the context stream): the 8 warps of a CTA take the SAME position of 8 different images
-// (imgs > 0), so the 12 KB of shift / scale per position come from L2 once per CTA and from L1 for the other seven warps;
-// with the natural row order every row pulled its own table rows through L2 (2x the bytes of x itself).  Measured on the
-// 96 LN launches of sampler step 0 (batch 64): 8.6 ms -> 6.95 ms; the context LN moves 302 MB in 76 us (4.0 TB/s, 61 % of
-// the measured HBM copy peak).  x is streamed (evict-first) so that it does not displace the tables.
-// (A persistent variant with the next row prefetched into registers -- 16 resident warps instead of 24 -- was slower:
-// 99 us for the same launch.)
-template <int MAXV>
+// (imgs > 0), so one shift / scale row (12 KB at D = 1536) serves the whole CTA; it is staged in shared memory with cp.async
+// while the x loads are in flight.  With the natural row order every row pulled its own table rows through L2 (2x the
+// bytes of x itself), one dependent pair at a time.  Measured on the 96 LN launches of sampler step 0 (batch 64):
+// 8.6 ms -> 6.95 ms (position-major) -> 6.1 ms (staged); the context LN moves 302 MB in 65 us (4.6 TB/s, 71 % of the measured
+// HBM copy peak), the image LN 151 MB in 34.6 us.  x is streamed (evict-first).
+// (A persistent variant with the next row prefetched into registers -- 16 resident warps instead of 24 -- was slower.)
+template <int MAXV, bool STAGED>   // STAGED: all 8 rows of the CTA use ONE shift / scale row, staged in shared memory
 __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x, int64_t ldx,
                                                      const float* __restrict__ shift, const float* __restrict__ scale,
                                                      int64_t ld_mod, int period, float* __restrict__ out_f32,
                                                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
                                                      int64_t ldo, int64_t M, int D, float eps, int fp16, int imgs) {
+  __shared__ __align__(16) float4 tab[STAGED ? 2 * MAXV * 32 : 1];     // [shift | scale] of the CTA's table row
   const int lane = threadIdx.x & 31;
+  const int nv = D >> 2;                              // float4 per row
   int64_t m;
+  bool active = true;
   if (imgs > 0) {
     const int64_t img = (int64_t)(blockIdx.x / period) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (img >= imgs) return;
+    active = img < imgs;
     m = img * period + (blockIdx.x % period);
   } else {
     m = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (m >= M) return;
+    active = m < M;
   }
-  const int nv = D >> 2;                              // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + m * ldx);
+  if (STAGED) {
+    // The table row goes global -> shared with cp.async (no registers), issued BEFORE the x loads so that both latencies
+    // overlap; read from L2 once per CTA.  Without this every row walked its 24 table float4 through L1/L2 one dependent
+    // pair at a time (12 serial round trips per row) and the kernel sat at 60 % of the HBM roofline.
+    const int64_t trow = (imgs > 0) ? (blockIdx.x % period) : 0;
+    const float4* sh = reinterpret_cast<const float4*>(shift + trow * ld_mod);
+    const float4* sc = reinterpret_cast<const float4*>(scale + trow * ld_mod);
+    for (int t = threadIdx.x; t < nv; t += blockDim.x) {
+      const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&tab[t]), d1 = (uint32_t)__cvta_generic_to_shared(&tab[MAXV * 32 + t]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(sh + t) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(sc + t) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else if (!active) {
+    return;
+  }
+  const float4* xr = reinterpret_cast<const float4*>(x + (active ? m : 0) * ldx);
   float4 v[MAXV];
   float sum = 0.f;
 #pragma unroll
@@ -205,17 +223,24 @@ __global__ void __launch_bounds__(256) ln_mod_kernel(const float* __restrict__ x
     }
   }
   const float rstd = rsqrtf(warp_sum(sq) / (float)D + eps);
-  const int64_t mrow = (period > 0) ? (m % period) : 0;
-  const float4* sh = shift ? reinterpret_cast<const float4*>(shift + mrow * ld_mod) : nullptr;
-  const float4* sc = scale ? reinterpret_cast<const float4*>(scale + mrow * ld_mod) : nullptr;
+  const float4 *sh = nullptr, *sc = nullptr;
+  if (STAGED) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!active) return;
+  } else if (shift) {
+    const int64_t mrow = (period > 0) ? (m % period) : 0;
+    sh = reinterpret_cast<const float4*>(shift + mrow * ld_mod);
+    sc = reinterpret_cast<const float4*>(scale + mrow * ld_mod);
+  }
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     int idx = lane + i * 32;
     if (idx < nv) {
       float4 y;
       y.x = (v[i].x - mean) * rstd; y.y = (v[i].y - mean) * rstd; y.z = (v[i].z - mean) * rstd; y.w = (v[i].w - mean) * rstd;
-      if (sc) {
-        float4 s4 = sc[idx], h4 = sh[idx];
+      if (STAGED || sc) {
+        const float4 h4 = STAGED ? tab[idx] : sh[idx], s4 = STAGED ? tab[MAXV * 32 + idx] : sc[idx];
         y.x = y.x * (1.f + s4.x) + h4.x; y.y = y.y * (1.f + s4.y) + h4.y;
         y.z = y.z * (1.f + s4.z) + h4.z; y.w = y.w * (1.f + s4.w) + h4.w;
       }
@@ -240,12 +265,14 @@ int launch_ln_mod(const float* x, int64_t ldx, const float* shift, const float* 
   // position-major mapping when the rows are [image][position] with per-position tables (see the kernel comment)
   const int imgs = (period > 1 && shift && M % period == 0 && M / period >= 2) ? (int)(M / period) : 0;
   dim3 grid(imgs ? (unsigned)(period * ((imgs + wpb - 1) / wpb)) : (unsigned)((M + wpb - 1) / wpb));
-  if (D <= 512)
-    ln_mod_kernel<4><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps, fp16, imgs);
-  else if (D <= 1536)
-    ln_mod_kernel<12><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps, fp16, imgs);
-  else
-    ln_mod_kernel<16><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps, fp16, imgs);
+  const bool staged = shift && (imgs > 0 || period <= 1);            // one table row per CTA
+#define STK_LN(MAXV, ST)                                                                                                      \
+  ln_mod_kernel<MAXV, ST><<<grid, wpb * 32, 0, s>>>(x, ldx, shift, scale, ld_mod, period, out_f32, out_hi, out_lo, ldo, M, D, eps, \
+                                                    fp16, imgs)
+  if (D <= 512) { if (staged) STK_LN(4, true); else STK_LN(4, false); }
+  else if (D <= 1536) { if (staged) STK_LN(12, true); else STK_LN(12, false); }
+  else { if (staged) STK_LN(16, true); else STK_LN(16, false); }
+#undef STK_LN
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;
