@@ -277,9 +277,10 @@ def run_gpu(args):
             ach = flops / (g_ms / 1000.0) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 kind::f16, %s)" % args.precision,
                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                    "traffic": 0.875e9 if B == BATCH else None, "traffic_unit": "bytes/launch",
-                    "traffic_source": "ncu --set full, dram__bytes_read+write of the 8 GEMMs of one layer at step 0 (3.50 GB), per grouped "
-                                      "launch (4 per layer); profiles/r1_gemm_tc2_kernel_ncu_full.md; algorithmic operand+output bytes 3.6 GB",
+                    "traffic": 1.013e9 if B == BATCH else None, "traffic_unit": "bytes/launch",
+                    "traffic_source": "ncu --set full, dram__bytes_read+write of the 4 grouped GEMM launches of one layer at step 0 "
+                                      "(4.05 GB), per launch; profiles/r1_layer_ncu_full_final.md; algorithmic operand+output bytes "
+                                      "3.38 GB per layer",
                     "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,
                     "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs)"}
