@@ -24,7 +24,7 @@ struct LinParams {
 };
 
 template <int BM, int BN>
-__global__ void __launch_bounds__(256) linear_f32_kernel(const LinParams p) {
+__global__ void __launch_bounds__(256, 2) linear_f32_kernel(const LinParams p) {
   constexpr int BK = 16;
   constexpr int TM = BM / 16, TN = BN / 16;          // 4 or 8
   constexpr int CM = TM / 4, CN = TN / 4;            // float4 chunks per thread
