@@ -277,10 +277,10 @@ def run_gpu(args):
             ach = flops / (g_ms / 1000.0) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 kind::f16, %s)" % args.precision,
                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                    "traffic": 1.013e9 if B == BATCH else None, "traffic_unit": "bytes/launch",
-                    "traffic_source": "ncu --set full, dram__bytes_read+write of the 4 grouped GEMM launches of one layer at step 0 "
-                                      "(4.05 GB), per launch; profiles/r1_layer_ncu_full_final.md; algorithmic operand+output bytes "
-                                      "3.38 GB per layer",
+                    "traffic": 0.906e9 if B == BATCH else None, "traffic_unit": "bytes/launch",
+                    "traffic_source": "ncu dram__bytes_read+write of the 4 grouped GEMM launches of one layer at step 0 (3.63 GB with the "
+                                      "evict_last hint on the weight tiles; 4.05 GB without), per launch; profiles/r1_layer_ncu_full_final.md; "
+                                      "algorithmic operand+output bytes 3.38 GB per layer",
                     "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,
                     "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs)"}
