@@ -125,3 +125,69 @@ def test_live_reference_agrees_if_mounted(tiny_sd):
     outs_q, tok, _ = O.encode(tiny_sd, C.TINY, x0)
     assert torch.equal(tok, tok_ref)
     assert (outs_q - outs_q_ref).abs().max() < 1e-5
+
+
+# ------------------------------------------------------------------ plain-C restatement of the index path (oracle/vq_oracle.c)
+def _c_oracle():
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from oracle import c_oracle
+    c_oracle.build()
+    return c_oracle
+
+
+def _enc_tensor(d, name):
+    sh, kind, std = synth.state_dict_spec(d)[name]
+    return synth.synth_tensor(name, sh, kind, std).numpy()
+
+
+def _check_ids(ids, ref_ids, ref_margin, what):
+    bad = np.nonzero(ids != ref_ids)[0]
+    for i in bad:                                       # only a rounding-level tie of the reference itself may differ
+        assert ref_margin[i] < 1e-6, f"{what}: id mismatch at {i} with reference margin {ref_margin[i]:.3e}"
+    if len(bad):
+        print(f"{what}: {len(bad)} ids differ, all at reference margins < 1e-6")
+
+
+def test_c_vq_restatement_matches_reference_fixture_tiny(gold):
+    """project_in + l2norm + cosine argmax (first maximum) + gather + final_layer_norm3, in plain C, against what the
+    unmodified reference produced from the same pre-VQ features (tests/golden/tiny.npz)."""
+    co = _c_oracle()
+    g, d = gold("tiny"), C.TINY
+    z = g["z"].reshape(-1, g["z"].shape[-1])
+    cb = _enc_tensor(d, "encoder.quantizer._codebook.embed")[0]
+    ids, _, margin = co.vq(z, _enc_tensor(d, "encoder.quantizer.project_in.weight"),
+                           _enc_tensor(d, "encoder.quantizer.project_in.bias"), cb)
+    _check_ids(ids, g["tokens"].reshape(-1), g["margin"].reshape(-1), "tiny")
+    assert np.abs(margin - g["margin"].reshape(-1)).max() < 1e-6
+    out = co.lookup_ln(g["tokens"].reshape(-1), cb, _enc_tensor(d, "encoder.final_layer_norm3.weight"),
+                       _enc_tensor(d, "encoder.final_layer_norm3.bias"))
+    assert np.abs(out - g["outs_q"].reshape(-1, out.shape[1])).max() < 2e-6
+
+
+def test_c_vq_restatement_matches_reference_fixture_full(gold):
+    """Full geometry (32768 x 16 codebook, 512 -> 16 projection): the fixture keeps the pre-VQ features of the first 8
+    tokens of each image."""
+    co = _c_oracle()
+    g, d = gold("full_encode"), C.FULL
+    z = g["z_sample"].reshape(-1, g["z_sample"].shape[-1])
+    n = g["z_sample"].shape[1]
+    cb = _enc_tensor(d, "encoder.quantizer._codebook.embed")[0]
+    ids, _, margin = co.vq(z, _enc_tensor(d, "encoder.quantizer.project_in.weight"),
+                           _enc_tensor(d, "encoder.quantizer.project_in.bias"), cb)
+    _check_ids(ids, g["tokens"][:, :n].reshape(-1), g["margin"][:, :n].reshape(-1), "full")
+    assert np.abs(margin - g["margin"][:, :n].reshape(-1)).max() < 1e-6
+    out = co.lookup_ln(g["tokens"].reshape(-1), cb, _enc_tensor(d, "encoder.final_layer_norm3.weight"),
+                       _enc_tensor(d, "encoder.final_layer_norm3.bias"))
+    assert np.abs(out - g["outs_q"].reshape(-1, out.shape[1])).max() < 2e-6
+
+
+@pytest.mark.parametrize("name,dims", [("tiny", C.TINY), ("full_encode", C.FULL)])
+def test_c_diti_schedule_matches_reference_fixture(gold, name, dims):
+    """k_i (visible-token limit per sampler step) as the reference's RectifiedFlow + DiTi_cont produced it."""
+    co = _c_oracle()
+    g = gold(name)
+    k = co.diti_k(g["timestep_map"].astype(np.int64), dims.stages, dims.k_per_stage, dims.K)
+    assert (k == g["k"]).all()
+    assert (k == S.make_tables(dims.K, dims.stages, dims.k_per_stage).k.numpy()).all()
