@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace stk {
 
@@ -189,13 +190,56 @@ __device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
   return r;
 }
 
+// (e0, e1) = 2^(s * scale + nsub) for a pair of scores WITHOUT the MUFU pipe: x = round(x) + f, f in [-0.5, 0.5];
+// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, three times below the half-ulp of the 16-bit P it
+// is rounded to right afterwards) on the packed fp32 pipe, 2^round(x) added straight into the exponent field.
+// round(x) comes from the 1.5 * 2^23 magic-number add (its low mantissa bits are the two's-complement integer), the
+// clamp keeps the exponent field from wrapping for x < -126 (result: a denormal, flushed to zero by the 16-bit convert).
+// SASS per pair: FFMA2, 3 x FADD2, 3 x FFMA2, 2 x VIMNMX, 2 x LEA -- no MUFU; x must be finite (unmasked tiles only).
+__device__ __forceinline__ void exp2_poly2(uint32_t s0, uint32_t s1, float scale, float nsub, float& e0, float& e1) {
+  uint32_t r0, r1;
+  asm("{\n\t.reg .b64 x, t, r, f, p, k;\n\t"
+      ".reg .b32 t0, t1, p0, p1;\n\t"
+      "mov.b64 x, {%2, %3};\n\t"
+      "mov.b64 k, {%4, %4};\n\t"
+      "mov.b64 r, {%5, %5};\n\t"
+      "fma.rn.f32x2 x, x, k, r;\n\t"
+      "mov.b64 k, {%6, %6};\n\t"
+      "add.rn.f32x2 t, x, k;\n\t"
+      "mov.b64 k, {%7, %7};\n\t"
+      "add.rn.f32x2 r, t, k;\n\t"
+      "sub.rn.f32x2 f, x, r;\n\t"
+      "mov.b64 k, {%8, %8};\n\t"
+      "mov.b64 p, {%9, %9};\n\t"
+      "fma.rn.f32x2 p, f, k, p;\n\t"
+      "mov.b64 k, {%10, %10};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"
+      "mov.b64 k, {%11, %11};\n\t"
+      "fma.rn.f32x2 p, p, f, k;\n\t"
+      "mov.b64 {t0, t1}, t;\n\t"
+      "mov.b64 {p0, p1}, p;\n\t"
+      "max.s32 t0, t0, %12;\n\t"
+      "max.s32 t1, t1, %12;\n\t"
+      "shl.b32 t0, t0, 23;\n\t"
+      "shl.b32 t1, t1, 23;\n\t"
+      "add.s32 %0, p0, t0;\n\t"
+      "add.s32 %1, p1, t1;\n\t}"
+      : "=r"(r0), "=r"(r1)
+      : "r"(s0), "r"(s1), "f"(scale), "f"(nsub), "f"(12582912.0f), "f"(-12582912.0f), "f"(0.05517132207751274f),
+        "f"(0.24261054396629333f), "f"(0.6932609677314758f), "f"(0.9999281167984009f), "r"(0x4B400000 - 126));
+  e0 = __uint_as_float(r0);
+  e1 = __uint_as_float(r1);
+}
+
 struct Attn5Params {
   AttnOut out;
   int B, S, H, ctx_rows, ctx_keys, fp16;
   float scale_log2e;
+  int rot;                 // per-round rotation of the item -> CTA map (load balance; see item_of)
 };
 
-template <bool FP16>
+// POLY: how many of the 16 score pairs a thread owns per tile take the polynomial exp2 (FMA pipe) instead of MUFU.EX2.
+template <bool FP16, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -226,6 +270,17 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   auto item_tiles = [&](int qt) {
     const int kmax_cta = ((qt + 1) * BQ <= p.ctx_rows) ? p.ctx_keys : S;  // every row of the tile is a context row
     return (kmax_cta + BKV - 1) / BKV;
+  };
+  // The CTA's n-th item: round n covers items [n G, (n + 1) G), and the CTA -> item map inside a round is rotated by
+  // n * rot.  Items differ in cost (the last query tile of a ragged S has idle softmax quarters, renderer context tiles see
+  // fewer keys), and with a fixed stride G a CTA would meet the same query tile every round whenever G % nq == 0; the host
+  // picks rot so that the query-tile index walks through all residues.  Neighbouring CTAs still hold neighbouring items.
+  const int G = (int)gridDim.x;
+  auto item_of = [&](int n) -> int {
+    const long long base = (long long)n * G;
+    if (base >= n_items) return -1;
+    const int it = (int)base + (int)(((long long)blockIdx.x + (long long)n * p.rot) % G);
+    return it < n_items ? it : -1;
   };
 
   if (warp == 1 && lane == 0) {
@@ -259,12 +314,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tma_load_2d(q_s + qb * Q_BYTES, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
       };
       int g = 0, n = 0;
-      if ((int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      if (item_of(0) >= 0) load_q(item_of(0), 0);
+      for (int item = item_of(0); item >= 0; item = item_of(++n)) {
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
         const int row0 = b * S;                                         // first row of this image in the [B*S, 3*H*64] matrix
         const int n_tiles = item_tiles(qt);
-        if (item + (int)gridDim.x < n_items) load_q(item + gridDim.x, n + 1);   // next item's Q, one item ahead
+        if (item_of(n + 1) >= 0) load_q(item_of(n + 1), n + 1);         // next item's Q, one item ahead
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % KV_STAGES;
           const uint32_t ph = (g / KV_STAGES) & 1;
@@ -295,17 +350,17 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (last) tc_commit(q_empty(qb));
       };
       int g = 0, n = 0;
-      if ((int)blockIdx.x < n_items) {
-        const int nt0 = item_tiles((int)blockIdx.x % nq);
+      if (item_of(0) >= 0) {
+        const int nt0 = item_tiles(item_of(0) % nq);
         issue_qk(0, 0, true, nt0 == 1);
       }
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      for (int item = item_of(0); item >= 0; item = item_of(++n)) {
         const int n_tiles = item_tiles(item % nq);
-        const int next = item + gridDim.x;
+        const int next = item_of(n + 1);
         for (int j = 0; j < n_tiles; ++j, ++g) {
           // look-ahead Q K^T (overlaps the softmax of tile g: S is double-buffered); crosses into the next item at the end
           if (j + 1 < n_tiles) issue_qk(n, g + 1, false, j + 2 == n_tiles);
-          else if (next < n_items) issue_qk(n + 1, g + 1, true, item_tiles(next % nq) == 1);
+          else if (next >= 0) issue_qk(n + 1, g + 1, true, item_tiles(next % nq) == 1);
           const int st = g % KV_STAGES;
           const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
           mbar_wait(p_ready(g & 1), (g >> 1) & 1);                       // P_g in TMEM, O rescaled (or read out), S[g & 1] consumed
@@ -360,86 +415,116 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             *reinterpret_cast<float4*>(of + o + c * 8 + 4) = make_float4(y[4], y[5], y[6], y[7]);
           }
           if (oh) {
-            uint16_t hh[8], ll[8];
+            uint32_t hp[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) split16(y[q], t.fp16 != 0, hh[q], ll[q]);
-            *reinterpret_cast<uint4*>(oh + o + c * 8) = make_uint4(hh[0] | ((uint32_t)hh[1] << 16), hh[2] | ((uint32_t)hh[3] << 16),
-                                                                   hh[4] | ((uint32_t)hh[5] << 16), hh[6] | ((uint32_t)hh[7] << 16));
-            if (ol) *reinterpret_cast<uint4*>(ol + o + c * 8) = make_uint4(ll[0] | ((uint32_t)ll[1] << 16), ll[2] | ((uint32_t)ll[3] << 16),
-                                                                           ll[4] | ((uint32_t)ll[5] << 16), ll[6] | ((uint32_t)ll[7] << 16));
+            for (int q = 0; q < 4; ++q) hp[q] = pack2_sat16(y[2 * q], y[2 * q + 1], FP16);
+            *reinterpret_cast<uint4*>(oh + o + c * 8) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            if (!FP16 && ol) {                                               // bf16 residual planes (split-bf16 consumers)
+              uint32_t lp[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) lp[q] = pack2_resid_bf16(y[2 * q], y[2 * q + 1], hp[q]);
+              *reinterpret_cast<uint4*>(ol + o + c * 8) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+            }
           }
         }
       }
     };
     int g = 0, n = 0, pend_item = -1, pend_g = 0;
     float pend_l = 1.f;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+    for (int item = item_of(0); item >= 0; item = item_of(++n)) {
       const int qt = item % nq;
       const int n_tiles = item_tiles(qt);
       const int row = qt * BQ + rl;
       const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
+      // Warp-uniform facts about this warp's 32 rows.  A quarter that lies entirely past the end of the sequence (the last
+      // query tile of a ragged S: S runs from 276 to 768 over the sampler schedule) does no softmax work at all -- its P / O
+      // rows are never stored -- it only keeps pace with the barriers.  Unmasked tiles (every key visible to every row of
+      // the warp) may take the polynomial exp2 path, which needs finite inputs.
+      const int wrow0 = qt * BQ + quarter * 32;
+      const bool warp_valid = wrow0 < S;
+      const int kmax_w = (wrow0 < p.ctx_rows) ? p.ctx_keys : S;           // smallest key limit of the warp's rows
       float m_run = -INFINITY, l_part = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++g) {
         mbar_wait(s_full(g & 1), (g >> 1) & 1);
-        tc_fence_after();
-        uint32_t r0[32];
-        tmem_ld32(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, r0);
-        tmem_ld_wait();
-        const int k0 = j * BKV + 32 * half;
-        if (k0 + 32 > kmax) {                                             // tile straddles this row's key limit
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + i >= kmax) r0[i] = 0xff800000u;                      // -inf
-        }
-        float mx;
-        {
-          float mp[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
-#pragma unroll
-          for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
-          mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
-        }
-        // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
-        xch[((g & 1) * 2 + half) * BQ + rl] = mx;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        mx = fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
-        // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays
-        // exact enough in 16 bits and the final O / l normalisation cancels the stale offset), so the O correction pass and
-        // its wait on the previous P V are rare instead of per tile.  (-inf - -inf = NaN keeps m_run: comparison is false.)
-        float m_new = fmaxf(m_run, mx * p.scale_log2e);
-        if (m_new - m_run <= kRescaleThreshold) m_new = m_run;
-        const float sub = (m_new == -INFINITY) ? 0.f : m_new;
-        const float corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-        // scale / subtract and the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2): the softmax warps are
-        // co-limited by issue slots and the MUFU pipe, so every instruction saved around the 32 ex2 counts
-        uint32_t w[16];
-        float rsp[4] = {0.f, 0.f, 0.f, 0.f};
-        const float nsub = -sub;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          float x0, x1;
-          scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
-          const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-          add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
-          w[q] = pack2_16(e0, e1, FP16);
-        }
-        const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
-        // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
-        tmem_st16(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, w);
-        l_part = l_part * corr + rs;
-        m_run = m_new;
-        // rescale this thread's 32 output dims only when some row of the warp moved its maximum
-        if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
-          mbar_wait(pv_done((g - 1) & 1), ((g - 1) >> 1) & 1);            // PV of the previous tile retired: O is stable
+        if (warp_valid) {
           tc_fence_after();
-          tmem_ld32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+          uint32_t r0[32];
+          tmem_ld32(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, r0);
           tmem_ld_wait();
+          const int k0 = j * BKV + 32 * half;
+          const bool masked_tile = k0 + 32 > kmax_w;                     // warp-uniform
+          if (k0 + 32 > kmax) {                                           // tile straddles this row's key limit
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
-          tmem_st32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+            for (int i = 0; i < 32; ++i)
+              if (k0 + i >= kmax) r0[i] = 0xff800000u;                    // -inf
+          }
+          float mx;
+          {
+            float mp[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
+#pragma unroll
+            for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
+            mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+          }
+          // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
+          xch[((g & 1) * 2 + half) * BQ + rl] = mx;
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          mx = fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
+          // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays
+          // exact enough in 16 bits and the final O / l normalisation cancels the stale offset), so the O correction pass and
+          // its wait on the previous P V are rare instead of per tile.  (-inf - -inf = NaN keeps m_run: comparison is false.)
+          float m_new = fmaxf(m_run, mx * p.scale_log2e);
+          if (m_new - m_run <= kRescaleThreshold) m_new = m_run;
+          const float sub = (m_new == -INFINITY) ? 0.f : m_new;
+          const float corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
+          // scale / subtract and the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2).  The 32 exponentials of
+          // a thread are what bounds the kernel (16 MUFU lanes per SM and clock against 906 M scores per launch at S = 768), so
+          // POLY of the 16 pairs -- spread evenly, the two pipes run side by side -- evaluate 2^x on the FMA pipe instead.
+          uint32_t w[16];
+          float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+          const float nsub = -sub;
+          if (POLY > 0 && !masked_tile) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float e0, e1;
+              if (((q * POLY) & 15) < POLY) {
+                exp2_poly2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, e0, e1);
+              } else {
+                float x0, x1;
+                scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
+                e0 = ex2_approx(x0); e1 = ex2_approx(x1);
+              }
+              add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
+              w[q] = pack2_16(e0, e1, FP16);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float x0, x1;
+              scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
+              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+              add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
+              w[q] = pack2_16(e0, e1, FP16);
+            }
+          }
+          const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
+          // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
+          tmem_st16(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, w);
+          l_part = l_part * corr + rs;
+          m_run = m_new;
+          // rescale this thread's 32 output dims only when some row of the warp moved its maximum
+          if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
+            mbar_wait(pv_done((g - 1) & 1), ((g - 1) >> 1) & 1);            // PV of the previous tile retired: O is stable
+            tc_fence_after();
+            tmem_ld32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
+            tmem_st32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+          }
+          tmem_st_wait();                                                   // P (and the rescaled O) are in TMEM
         }
-        tmem_st_wait();                                                   // P (and the rescaled O) are in TMEM
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_ready(g & 1));
@@ -449,11 +534,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         }
       }
       // ---- item end: combine the partial row sums now, leave the read-out of O for after the next item's first tile
-      xch[(4 + half) * BQ + rl] = l_part;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      pend_l = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
-      pend_item = item;
-      pend_g = g - 1;
+      if (warp_valid) {
+        xch[(4 + half) * BQ + rl] = l_part;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        pend_l = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
+        pend_item = item;
+        pend_g = g - 1;
+      }
     }
     if (pend_item >= 0) epilogue(pend_item, n - 1, pend_g, pend_l);
   }
@@ -465,33 +552,63 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
-bool g_attr_set = false;
-int g_num_sms = 148;
+typedef void (*Attn5Fn)(const CUtensorMap, const CUtensorMap, const Attn5Params);
+// polynomial-exp2 pairs per thread and tile (of 16): the default balances the MUFU and FMA / issue budgets (see the kernel);
+// SELFTOK_ATTN_POLY = 0 | 4 | 5 | 6 | 8 selects another instantiation for A/B runs
+constexpr int kPolyDefault = 5;
+template <bool FP16>
+Attn5Fn attn5_fn(int poly) {
+  switch (poly) {
+    case 0: return attention_tc5_kernel<FP16, 0>;
+    case 4: return attention_tc5_kernel<FP16, 4>;
+    case 6: return attention_tc5_kernel<FP16, 6>;
+    case 8: return attention_tc5_kernel<FP16, 8>;
+    default: return attention_tc5_kernel<FP16, 5>;
+  }
+}
+int g_poly = -1;
+int g_num_sms_dev[64];
+bool g_attr_dev[64];       // cudaFuncSetAttribute is per device: one handle per GPU may live in the same process
+
+int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 }  // namespace
+
+void attention_tc5_set_poly(int pairs) { g_poly = pairs; }
 
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16) {
   STK_CHECK(qkv16 && B > 0 && S > 0 && H > 0, -1, "attention_tc5: bad arguments");
   STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
+  STK_CHECK(ctx_keys <= S && ctx_rows <= S, -1, "attention_tc5: context limits exceed the sequence");
   STK_TRY(gemm_tc_init());
-  if (!g_attr_set) {
-    int dev = 0;
-    STK_CUDA(cudaGetDevice(&dev));
-    STK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    g_attr_set = true;
+  if (g_poly < 0) {
+    const char* v = getenv("SELFTOK_ATTN_POLY");
+    g_poly = v ? atoi(v) : kPolyDefault;
+  }
+  int dev = 0;
+  STK_CUDA(cudaGetDevice(&dev));
+  STK_CHECK(dev >= 0 && dev < 64, -1, "attention_tc5: device ordinal out of range");
+  Attn5Fn fn = fp16 ? attn5_fn<true>(g_poly) : attn5_fn<false>(g_poly);
+  if (!g_attr_dev[dev]) {
+    STK_CUDA(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
+    for (int pl : {0, 4, 5, 6, 8}) {
+      STK_CUDA(cudaFuncSetAttribute(attn5_fn<true>(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      STK_CUDA(cudaFuncSetAttribute(attn5_fn<false>(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
+    g_attr_dev[dev] = true;
   }
   CUtensorMap mq, mkv;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)3 * H * HD;
   STK_TRY(make_tensor_map_2d(&mq, qkv16, rows, cols, BQ, HD, fp16));
   STK_TRY(make_tensor_map_2d(&mkv, qkv16, rows, cols, BKV, HD, fp16));
-  Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
-  const int n_items = ((S + BQ - 1) / BQ) * H * B;
-  dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
-  if (fp16) attention_tc5_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
-  else attention_tc5_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  const int nq = (S + BQ - 1) / BQ;
+  const int n_items = nq * H * B;
+  const int grid = std::min(n_items, 2 * g_num_sms_dev[dev]);      // persistent: two CTAs per SM walk the item list
+  int rot = 0;                                                     // smallest rotation that makes the query-tile walk full-period
+  while (gcd_i((grid + rot) % nq == 0 ? nq : (grid + rot) % nq, nq) != 1 && rot < nq) ++rot;
+  Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f, rot};
+  fn<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

@@ -139,4 +139,20 @@ __device__ __forceinline__ void split16(float x, bool fp16, uint16_t& hi, uint16
   }
 }
 
+// two fp32 -> one packed 16-bit pair (lo in bits 0-15): IEEE half with saturation to +-65504 (one F2FP.SATFINITE instead of
+// two clamps + convert), or bf16 round-to-nearest
+__device__ __forceinline__ uint32_t pack2_sat16(float lo, float hi, bool fp16) {
+  uint32_t r;
+  if (fp16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// bf16 residual plane of a pair: lo = rn(x - rn_bf16(x))
+__device__ __forceinline__ uint32_t pack2_resid_bf16(float a, float b, uint32_t hi_pair) {
+  const float ra = a - __uint_as_float(hi_pair << 16), rb = b - __uint_as_float(hi_pair & 0xffff0000u);
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(rb), "f"(ra));
+  return r;
+}
+
 }  // namespace stk

@@ -657,9 +657,14 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       // ---- tensor-core path: the two streams' GEMMs of every stage share one launch (lintc2)
       const int fp16 = is_fp16(e);
       const float* lm = e->ctx_last_mod + (int64_t)step * 2 * D;                // last layer: pre_only (shift, scale) from c
-      if (!last) PROF(PC_LN, launch_ln_mod(w.ctx, D, cmod, cmod + D, 6 * D, Kc, nullptr, w.a_c_hi, w.a_c_lo, D, Mc, D, 1e-6f, s, fp16));
-      else PROF(PC_LN, launch_ln_mod(w.ctx, D, lm, lm + D, 2 * D, 1, nullptr, w.a_c_hi, w.a_c_lo, D, Mc, D, 1e-6f, s, fp16));
-      PROF(PC_LN, launch_ln_mod(w.x, D, xmod, xmod + D, 6 * D, 1, nullptr, w.a_x_hi, w.a_x_lo, D, Mx, D, 1e-6f, s, fp16));
+      // LN + modulate of both streams in one launch (context rows: per-position adaLN table; image rows: the step's row)
+      LnProblem lp[2];
+      lp[0].x = w.ctx; lp[0].out_hi = w.a_c_hi; lp[0].out_lo = w.a_c_lo; lp[0].M = Mc;
+      if (!last) { lp[0].shift = cmod; lp[0].scale = cmod + D; lp[0].ld_mod = 6 * D; lp[0].period = Kc; }
+      else { lp[0].shift = lm; lp[0].scale = lm + D; lp[0].ld_mod = 2 * D; lp[0].period = 1; }
+      lp[1].x = w.x; lp[1].out_hi = w.a_x_hi; lp[1].out_lo = w.a_x_lo; lp[1].M = Mx;
+      lp[1].shift = xmod; lp[1].scale = xmod + D; lp[1].ld_mod = 6 * D; lp[1].period = 1;
+      PROF(PC_LN, launch_ln_mod_pair(lp, 2, D, 1e-6f, s, fp16));
       TcProblem pr[2];
       Epilogue eq;                                                              // q/k/v leave the GEMM as 16-bit planes in the joint buffer
       eq.mode = EPI_SPLIT; eq.out_hi = w.qkv_hi; eq.out_lo = w.qkv_lo; eq.ldo = 3 * D; eq.rpb_out = S;
@@ -685,8 +690,10 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       if (!last) STK_TRY(tc_problem(e, pc + "attn.proj", w.attn_c_hi, w.attn_c_lo, Mc, erc, &pr[np++]));
       STK_TRY(tc_problem(e, px + "attn.proj", w.attn_x_hi, w.attn_x_lo, Mx, erx, &pr[np++]));
       STK_TRY(lintc2(e, pr, np, s));
-      if (!last) PROF(PC_LN, launch_ln_mod(w.ctx, D, cmod + 3 * D, cmod + 4 * D, 6 * D, Kc, nullptr, w.a_c_hi, w.a_c_lo, D, Mc, D, 1e-6f, s, fp16));
-      PROF(PC_LN, launch_ln_mod(w.x, D, xmod + 3 * D, xmod + 4 * D, 6 * D, 1, nullptr, w.a_x_hi, w.a_x_lo, D, Mx, D, 1e-6f, s, fp16));
+      lp[0].shift = cmod + 3 * D; lp[0].scale = cmod + 4 * D; lp[0].ld_mod = 6 * D; lp[0].period = Kc;
+      lp[1].shift = xmod + 3 * D; lp[1].scale = xmod + 4 * D;
+      if (!last) PROF(PC_LN, launch_ln_mod_pair(lp, 2, D, 1e-6f, s, fp16));
+      else PROF(PC_LN, launch_ln_mod_pair(lp + 1, 1, D, 1e-6f, s, fp16));
       Epilogue ehc, ehx;
       ehc.mode = EPI_SPLIT; ehc.act = ACT_GELU; ehc.out_hi = w.h_c_hi; ehc.out_lo = w.h_c_lo; ehc.ldo = 4 * D;
       ehx = ehc; ehx.out_hi = w.h_x_hi; ehx.out_lo = w.h_x_lo;
@@ -970,6 +977,13 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_linear_tc(const 
 extern "C" __attribute__((visibility("default"))) int selftok_k_set_gemm_ctas(int n) {
   STK_CHECK(n == 1 || n == 2, SELFTOK_ERR_BAD_ARG, "selftok_k_set_gemm_ctas: n must be 1 or 2");
   gemm_tc_set_ctas(n);
+  return SELFTOK_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int selftok_k_set_attn_poly(int pairs) {
+  STK_CHECK(pairs == 0 || pairs == 4 || pairs == 5 || pairs == 6 || pairs == 8, SELFTOK_ERR_BAD_ARG,
+            "selftok_k_set_attn_poly: pairs must be 0, 4, 5, 6 or 8");
+  attention_tc5_set_poly(pairs);
   return SELFTOK_OK;
 }
 

@@ -133,17 +133,7 @@ constexpr int EPI_STAGE_FLOATS = 32 * 32;
 constexpr int EPI_WARPS = 8;
 __device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 // two fp32 -> packed 16-bit pair (IEEE half, saturating, or bf16): one cvt per pair
-__device__ __forceinline__ uint32_t pack2(float lo, float hi, bool fp16) {
-  uint32_t r;
-  if (fp16) {
-    lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-    hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  } else {
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  }
-  return r;
-}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, bool fp16) { return pack2_sat16(lo, hi, fp16); }
 // MODE / GELU are compile-time so that the per-element path carries no mode branches; the arithmetic of all 8 row passes
 // of a chunk is issued unconditionally (independent chains -> ILP) and only the global stores are predicated.
 template <int MODE, bool GELU>
@@ -464,12 +454,16 @@ __device__ __forceinline__ void tc_mma_f16_2sm(uint32_t d_tmem, uint64_t a_desc,
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// arrive on the barrier at the same offset in CTA `rank` of the cluster
+// arrive on the barrier at the same offset in CTA `rank` of the cluster.  Default semantics (.release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive: the barrier only hands the TMEM accumulator back to the MMA issuer, and the TMEM reads
+// are already complete (tcgen05.wait::ld) and ordered (tcgen05.fence::before_thread_sync).  The explicit .release.cluster
+// form used in round 1 compiled to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive -- it drained the warp's
+// outstanding global stores first and held 6-9 % of all warp samples in every GEMM (profiles/r1_layer_ncu_full_final.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(local_bar), "r"(rank) : "memory");
 }
 
@@ -649,7 +643,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 0;
+// per-device state: cudaFuncSetAttribute and the SM count belong to a device, and one process may hold a handle per GPU
+constexpr int kMaxDev = 64;
+int g_num_sms_dev[kMaxDev];
+bool g_attr_dev[kMaxDev];
 int g_gemm_ctas = 2;      // 2: cta_group::2 pair kernel (default); 1: single-CTA kernel (SELFTOK_GEMM_CTAS=1)
 
 int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, int box_rows, int fp16) {
@@ -689,22 +686,28 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 void gemm_tc_set_ctas(int n) { g_gemm_ctas = n == 1 ? 1 : 2; }
 
+// Idempotent per device (the current one): resolves cuTensorMapEncodeTiled once per process, opts the kernels into their
+// dynamic shared memory and records the SM count once per device.
 int gemm_tc_init() {
-  if (g_encode) return 0;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult qres;
-  STK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-  STK_CHECK(fn && qres == cudaDriverEntryPointSuccess, -5, "cuTensorMapEncodeTiled not available from the driver");
   int dev = 0;
   STK_CUDA(cudaGetDevice(&dev));
-  STK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  STK_CHECK(dev >= 0 && dev < kMaxDev, -1, "gemm_tc: device ordinal out of range");
+  if (g_encode && g_attr_dev[dev]) return 0;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    STK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    STK_CHECK(fn && qres == cudaDriverEntryPointSuccess, -5, "cuTensorMapEncodeTiled not available from the driver");
+    const char* v = getenv("SELFTOK_GEMM_CTAS");
+    if (v) g_gemm_ctas = atoi(v) == 1 ? 1 : 2;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  STK_CUDA(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
   STK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<1>::SMEM_BYTES));
   STK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<3>::SMEM_BYTES));
   STK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<1>::SMEM_BYTES));
   STK_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2<3>::SMEM_BYTES));
-  const char* v = getenv("SELFTOK_GEMM_CTAS");
-  if (v) g_gemm_ctas = atoi(v) == 1 ? 1 : 2;
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  g_attr_dev[dev] = true;
   return 0;
 }
 
@@ -737,8 +740,11 @@ static int make_maps(TcMaps* m, const TcProblem& q, int nsplit, int fp16, int b_
 // One launch for up to two independent problems (the context- and the image-stream GEMM of an MMDiT layer): their tiles share
 // the persistent grid, so the small N = 1536 GEMMs no longer pay a partially filled last wave each.
 int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream_t s, int fp16) {
-  STK_CHECK(g_encode, -3, "gemm_tc_init has not been called");
+  STK_TRY(gemm_tc_init());                                // no-op after the first call on this device
   STK_CHECK(probs && (n == 1 || n == 2), -1, "gemm_tc: one or two problems per launch");
+  int dev = 0;
+  STK_CUDA(cudaGetDevice(&dev));
+  const int g_num_sms = g_num_sms_dev[dev];
   for (int i = 0; i < n; ++i) STK_TRY(check_problem(probs[i], nsplit, fp16));
   const bool pair = g_gemm_ctas == 2 && g_num_sms >= 2;
   if (!pair) {                                            // single-CTA bisecting kernel: one launch per problem

@@ -38,6 +38,21 @@ int launch_linear_f32(const float* A, int64_t lda, const float* W, int64_t ldw, 
 int launch_ln_mod(const float* x, int64_t ldx, const float* shift, const float* scale, int64_t ld_mod, int period,
                   float* out_f32, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int64_t ldo, int64_t M, int D,
                   float eps, cudaStream_t s, int fp16 = 0);
+// Two LN + modulate problems (the context- and the image-row pass of one MMDiT layer stage) in ONE launch, 16-bit plane
+// output (IEEE half when fp16, else bf16 hi [+ lo]).  period > 1: rows are [image][position] with a per-position table row
+// (M must be a multiple of period); period <= 1: one table row for all rows.
+struct LnProblem {
+  const float* x = nullptr;          // [M, D] fp32, contiguous rows
+  const float* shift = nullptr;
+  const float* scale = nullptr;
+  int64_t ld_mod = 0;
+  int period = 1;
+  __nv_bfloat16* out_hi = nullptr;
+  __nv_bfloat16* out_lo = nullptr;
+  int64_t M = 0;
+  int imgs = 0;                      // filled by the launcher
+};
+int launch_ln_mod_pair(const LnProblem* probs, int n, int D, float eps, cudaStream_t s, int fp16);
 // Attention output routing: query rows [0,split) of every image go to the compact buffer A ([B*split, ld]),
 // rows [split,Sq) to buffer B ([B*(Sq-split), ld]).  split == Sq -> everything in A.  Each buffer is fp32 and/or
 // bf16 hi(/lo) planes (NULL pointers are skipped).
@@ -95,6 +110,7 @@ int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo
                         int ctx_rows, int ctx_keys, const AttnOut& out, cudaStream_t s, int fp16 = 0);
 
 // tcgen05 / TMEM attention (attn_tc5.cu), single-pass 16-bit operands (fp16 != 0: IEEE half, else bf16)
+void attention_tc5_set_poly(int pairs);   // 0 | 4 | 5 | 6 | 8 polynomial-exp2 pairs of 16 (A/B switch)
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16);
 

@@ -278,6 +278,131 @@ int launch_ln_mod(const float* x, int64_t ldx, const float* shift, const float* 
   return 0;
 }
 
+// ---- the two LN + modulate passes of an MMDiT layer stage (context rows, image rows) in ONE launch, 16-bit plane output.
+// Each CTA = 8 rows that share one shift / scale table row (staged in shared memory with cp.async under the x loads):
+// context problem position-major (the same position of 8 images), image problem natural order with its single per-step row.
+// One launch instead of two keeps the small late-schedule launches (B * Kc rows with Kc down to 20) from each leaving most
+// of the 148 SMs idle, and the output mode is compile-time (no per-element branches; one saturating F2FP per pair).
+struct LnPairParams {
+  LnProblem pr[2];
+  int nblk0;               // CTAs of problem 0 (problem 1 owns the rest of the grid)
+  int D;
+  float eps;
+};
+
+template <int MAXV, bool FP16, bool LO>
+__global__ void __launch_bounds__(256) ln_mod_pair_kernel(const LnPairParams p) {
+  __shared__ __align__(16) float4 tab[2 * MAXV * 32];
+  const bool second = (int)blockIdx.x >= p.nblk0;
+  const LnProblem& q = second ? p.pr[1] : p.pr[0];
+  const int blk = second ? (int)blockIdx.x - p.nblk0 : (int)blockIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nv = p.D >> 2;
+  int64_t m, trow;
+  bool active;
+  if (q.imgs > 0) {                                    // position-major: row = img * period + pos
+    const int64_t img = (int64_t)(blk / q.period) * 8 + wid;
+    active = img < q.imgs;
+    trow = blk % q.period;
+    m = img * q.period + trow;
+  } else {                                             // natural order, one table row for the whole problem
+    m = (int64_t)blk * 8 + wid;
+    active = m < q.M;
+    trow = 0;
+  }
+  {
+    const float4* sh = reinterpret_cast<const float4*>(q.shift + trow * q.ld_mod);
+    const float4* sc = reinterpret_cast<const float4*>(q.scale + trow * q.ld_mod);
+    for (int t = threadIdx.x; t < nv; t += 256) {
+      const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(&tab[t]), d1 = (uint32_t)__cvta_generic_to_shared(&tab[MAXV * 32 + t]);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(sh + t) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(sc + t) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const float4* xr = reinterpret_cast<const float4*>(q.x + (active ? m : 0) * (int64_t)p.D);
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      v[i] = __ldcs(xr + idx);
+      sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(sum) / (float)p.D;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)p.D + p.eps);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (!active) return;
+  uint2* oh = reinterpret_cast<uint2*>(q.out_hi + m * (int64_t)p.D);
+  uint2* ol = LO ? reinterpret_cast<uint2*>(q.out_lo + m * (int64_t)p.D) : nullptr;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 h4 = tab[idx], s4 = tab[MAXV * 32 + idx];
+      float4 y;
+      y.x = (v[i].x - mean) * rstd; y.y = (v[i].y - mean) * rstd; y.z = (v[i].z - mean) * rstd; y.w = (v[i].w - mean) * rstd;
+      y.x = y.x * (1.f + s4.x) + h4.x; y.y = y.y * (1.f + s4.y) + h4.y;
+      y.z = y.z * (1.f + s4.z) + h4.z; y.w = y.w * (1.f + s4.w) + h4.w;
+      const uint32_t p0 = pack2_sat16(y.x, y.y, FP16), p1 = pack2_sat16(y.z, y.w, FP16);
+      oh[idx] = make_uint2(p0, p1);
+      if (LO) ol[idx] = make_uint2(pack2_resid_bf16(y.x, y.y, p0), pack2_resid_bf16(y.z, y.w, p1));
+    }
+  }
+}
+
+int launch_ln_mod_pair(const LnProblem* probs, int n, int D, float eps, cudaStream_t s, int fp16) {
+  STK_CHECK(probs && (n == 1 || n == 2) && D > 0 && D % 4 == 0 && D <= 2048, -1, "ln_mod_pair: bad arguments");
+  LnPairParams p;
+  p.D = D; p.eps = eps;
+  int nblk[2] = {0, 0};
+  bool lo = false;
+  for (int i = 0; i < 2; ++i) {
+    if (i >= n) { p.pr[i] = probs[0]; p.pr[i].M = 0; continue; }
+    LnProblem q = probs[i];
+    STK_CHECK(q.x && q.shift && q.scale && q.out_hi && q.M > 0 && q.ld_mod % 4 == 0, -1, "ln_mod_pair: bad problem");
+    STK_CHECK(i == 0 || (q.out_lo != nullptr) == lo, -1, "ln_mod_pair: both problems must use the same plane set");
+    lo = q.out_lo != nullptr;
+    if (q.period > 1) {                                // per-position table: position-major, needs whole images
+      STK_CHECK(q.M % q.period == 0, -1, "ln_mod_pair: rows must be whole images of `period` positions");
+      q.imgs = (int)(q.M / q.period);
+      nblk[i] = q.period * ((q.imgs + 7) / 8);
+    } else {
+      q.period = 1; q.imgs = 0;
+      nblk[i] = (int)((q.M + 7) / 8);
+    }
+    p.pr[i] = q;
+  }
+  STK_CHECK(!(fp16 && lo), -1, "ln_mod_pair: the fp16 mode has no residual planes");
+  p.nblk0 = nblk[0];
+  const unsigned grid = (unsigned)(nblk[0] + nblk[1]);
+#define STK_LNP(MAXV)                                                                       \
+  do {                                                                                      \
+    if (fp16) ln_mod_pair_kernel<MAXV, true, false><<<grid, 256, 0, s>>>(p);                \
+    else if (lo) ln_mod_pair_kernel<MAXV, false, true><<<grid, 256, 0, s>>>(p);             \
+    else ln_mod_pair_kernel<MAXV, false, false><<<grid, 256, 0, s>>>(p);                    \
+  } while (0)
+  if (D <= 512) STK_LNP(4);
+  else if (D <= 1536) STK_LNP(12);
+  else STK_LNP(16);
+#undef STK_LNP
+  count_launch();
+  STK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // =================================================================================================== attention (fp32)
 // One CTA = 64 queries of one (batch, head); 256 threads as 16 x 16; keys streamed in tiles of 64 with an online
 // softmax.  S-phase: thread (ty,tx) owns rows ty*4..+3 x keys tx*4..+3; PV-phase: rows ty*4..+3 x dims tx*(HD/16)..
@@ -444,8 +569,13 @@ int launch_attention_f32(const float* q, int64_t q_ld, int64_t q_bs, const float
   dim3 grid((Sq + 63) / 64, H, B);
   size_t smem = sizeof(float) * (size_t)(hd * 68 * 2 + 64 * hd + 64 * 68);
   if (hd == 64) {
-    static bool attr = false;
-    if (!attr) { STK_CUDA(cudaFuncSetAttribute(attention_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static bool attr[64];                                        // per device (one handle per GPU may share the process)
+    int dev = 0;
+    STK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr[dev]) {
+      STK_CUDA(cudaFuncSetAttribute(attention_f32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr[dev] = true;
+    }
     attention_f32_kernel<64><<<grid, 256, smem, s>>>(p);
   } else if (hd == 32) {
     attention_f32_kernel<32><<<grid, 256, smem, s>>>(p);
