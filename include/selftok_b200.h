@@ -157,9 +157,6 @@ int selftok_k_linear_tc(const float* A_dev, const float* W_dev, const float* bia
                         int64_t M, int N, int K, int nsplit, void* stream);
 /* Process-wide choice of the tcgen05 GEMM variant: 2 = cta_group::2 SM-pair kernel (default), 1 = single-CTA kernel. */
 int selftok_k_set_gemm_ctas(int n);
-/* Process-wide: how many of the 16 score pairs per thread and tile the tcgen05 attention evaluates with the polynomial
- * exp2 on the FMA pipe instead of MUFU.EX2 (0, 4, 5, 6 or 8; default 5).  A/B switch for profiles/ab_attention.py. */
-int selftok_k_set_attn_poly(int pairs);
 /* out = LN(x) * (1 + scale[m % period]) + shift[m % period], rows of D; eps 1e-6, no affine. */
 int selftok_k_ln_mod_f32(const float* x_dev, const float* shift_dev, const float* scale_dev, int64_t ld_mod,
                          int period, float* out_dev, int64_t M, int D, void* stream);

@@ -123,6 +123,67 @@ def lookup(pipe, tokens):
     return o
 
 
+# ---------------------------------------------------------------------------------------------- pixel boundary (SD3 VAE)
+def ref_vae(ch):
+    """The reference's in-tree SD3 VAE (`SDVAE`, sd3/sd3_impls.py:447-474) in fp32 on the CPU with the seeded synthetic
+    VAE checkpoint -- the stand-in BASELINE.md prescribes for pixel-space parity (no SD3 weights can be fetched)."""
+    ref_loader.import_reference()
+    from mimogpt.models.selftok.sd3.sd3_impls import VAEDecoder, VAEEncoder
+
+    class _VAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            with ref_loader.skip_init():
+                self.encoder = VAEEncoder(ch=ch)
+                self.decoder = VAEDecoder(ch=ch)
+
+    m = _VAE()
+    m.load_state_dict(synth.synth_vae_state_dict(ch=ch), strict=True)
+    return m.eval()
+
+
+def ref_pixels(vae, pred_x0):
+    """The pixel end of SelftokPipeline.decoding (SelftokPipeline.py:284-294) with the reference's own helpers."""
+    from mimogpt.models.selftok.sd3.sd3_impls import SD3LatentFormat
+    from mimogpt.infer.SelftokPipeline import norm_ip
+    with torch.no_grad():
+        rec = vae.decoder(SD3LatentFormat().process_out(pred_x0.float()))
+    norm_ip(rec, -1, 1)
+    return rec
+
+
+def gen_vae_tiny():
+    """Pins oracle/vae_oracle.py: decoder and encoder of the reference SDVAE at ch = 32 on seeded inputs."""
+    vae = ref_vae(32)
+    z = synth.synth_tensor("golden.vae.z", (2, 16, 8, 8), "emb", 1.0)
+    x = synth.synth_tensor("golden.vae.x", (2, 3, 64, 64), "emb", 0.5)
+    with torch.no_grad():
+        dec = vae.decoder(z)
+        mom = vae.encoder(x)
+    save("vae_tiny", dec=dec, moments=mom)
+
+
+def gen_pixels_tiny():
+    """Pixel fixture of the reduced geometry: the reference's own 50-step result (tests/golden/tiny.npz) through the
+    reference SDVAE (ch = 32) exactly as SelftokPipeline.decoding finishes (process_out -> vae.decode -> norm_ip)."""
+    g = np.load(os.path.join(GOLD, "tiny.npz"))
+    vae = ref_vae(32)
+    save("tiny_pixels", pixels=ref_pixels(vae, torch.from_numpy(g["pred_x0"])))
+
+
+def gen_pixels_full():
+    """Full geometry, B = 1: reference latents of tests/golden/full_decode.npz and full_renderer.npz through the
+    full-size (ch = 128) reference SDVAE -> [1,3,256,256] pixels in [0,1]."""
+    vae = ref_vae(128)
+    g = np.load(os.path.join(GOLD, "full_decode.npz"))
+    gr = np.load(os.path.join(GOLD, "full_renderer.npz"))
+    t0 = time.time()
+    px = ref_pixels(vae, torch.from_numpy(g["pred_x0"]))
+    pr = ref_pixels(vae, torch.from_numpy(gr["pred_x0"]))
+    print(f"SDVAE decode of 2 images: {time.time() - t0:.1f}s; in-range fraction {float(((px > 0) & (px < 1)).float().mean()):.3f}")
+    save("full_pixels", pixels=px, renderer_pixels=pr)
+
+
 def save(name, **arrs):
     os.makedirs(GOLD, exist_ok=True)
     out = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrs.items()}
@@ -234,5 +295,11 @@ if __name__ == "__main__":
             gen_full_decode(pipe)
         elif w == "full_renderer":
             gen_full_renderer()
+        elif w == "vae_tiny":
+            gen_vae_tiny()
+        elif w == "tiny_pixels":
+            gen_pixels_tiny()
+        elif w == "full_pixels":
+            gen_pixels_full()
         else:
             raise SystemExit(f"unknown target {w}")

@@ -2,13 +2,14 @@
 # Build a variant library for same-box A/B runs:   profiles/mk_variant.sh <name> <file.cu> [<file.cu> ...]
 # Each given .cu replaces the in-tree source of the same role (its basename must start with attn_tc5 / gemm_tc / kernels_simt /
 # attn_tc / engine, e.g. build/ab/gemm_tc_hint.cu); everything else links from the in-tree objects (run the normal build first).
+# EXTRA="-DFOO" adds compiler flags (macro-selected variants of an in-tree source).
 # Result: build/ab/lib_<name>.so  ->  SELFTOK_B200_LIB=$PWD/build/ab/lib_<name>.so python profiles/step_classes.py
 set -e
 name=$1; shift
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
 C=$ROOT/selftoktokenizer_b200/csrc
 mkdir -p $ROOT/build/ab
-F="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -I$C -diag-suppress 177"
+F="$EXTRA -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -I$C -diag-suppress 177"
 declare -A obj=( [kernels_simt]=$C/kernels_simt.o [gemm_tc]=$C/gemm_tc.o [attn_tc]=$C/attn_tc.o [attn_tc5]=$C/attn_tc5.o [engine]=$C/engine.o )
 for src in "$@"; do
   b=$(basename $src .cu)

@@ -25,7 +25,7 @@ SYMBOLS = [
     "selftok_set_schedule", "selftok_finalize", "selftok_encode", "selftok_vq_argmax", "selftok_lookup",
     "selftok_decode", "selftok_dit_velocity", "selftok_render", "selftok_encode_host", "selftok_decode_host",
     "selftok_render_host", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
-    "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_set_gemm_ctas", "selftok_k_set_attn_poly", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
+    "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_set_gemm_ctas", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
     "selftok_k_attention_tc",
 ]
 
@@ -81,7 +81,6 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.selftok_k_linear_f32.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
     lib.selftok_k_linear_tc.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, vp]
     lib.selftok_k_set_gemm_ctas.argtypes = [i32]
-    lib.selftok_k_set_attn_poly.argtypes = [i32]
     lib.selftok_k_ln_mod_f32.argtypes = [vp, vp, vp, i64, i32, vp, i64, i32, vp]
     lib.selftok_k_attention_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, i64, i32, vp, i64, i32, i32, i32, i32, vp]
     lib.selftok_k_attention_tc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
@@ -311,10 +310,6 @@ def k_linear_tc(A, W, bias=None, nsplit=3):
 
 def k_set_gemm_ctas(n: int) -> None:
     check(load_library().selftok_k_set_gemm_ctas(n))
-
-
-def k_set_attn_poly(pairs: int) -> None:
-    check(load_library().selftok_k_set_attn_poly(pairs))
 
 
 def k_ln_mod_f32(x, shift=None, scale=None, period=1):

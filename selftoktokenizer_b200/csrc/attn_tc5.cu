@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 
 namespace stk {
@@ -190,47 +191,6 @@ __device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
   return r;
 }
 
-// (e0, e1) = 2^(s * scale + nsub) for a pair of scores WITHOUT the MUFU pipe: x = round(x) + f, f in [-0.5, 0.5];
-// 2^f by a degree-3 minimax polynomial (max relative error 7.5e-5, three times below the half-ulp of the 16-bit P it
-// is rounded to right afterwards) on the packed fp32 pipe, 2^round(x) added straight into the exponent field.
-// round(x) comes from the 1.5 * 2^23 magic-number add (its low mantissa bits are the two's-complement integer), the
-// clamp keeps the exponent field from wrapping for x < -126 (result: a denormal, flushed to zero by the 16-bit convert).
-// SASS per pair: FFMA2, 3 x FADD2, 3 x FFMA2, 2 x VIMNMX, 2 x LEA -- no MUFU; x must be finite (unmasked tiles only).
-__device__ __forceinline__ void exp2_poly2(uint32_t s0, uint32_t s1, float scale, float nsub, float& e0, float& e1) {
-  uint32_t r0, r1;
-  asm("{\n\t.reg .b64 x, t, r, f, p, k;\n\t"
-      ".reg .b32 t0, t1, p0, p1;\n\t"
-      "mov.b64 x, {%2, %3};\n\t"
-      "mov.b64 k, {%4, %4};\n\t"
-      "mov.b64 r, {%5, %5};\n\t"
-      "fma.rn.f32x2 x, x, k, r;\n\t"
-      "mov.b64 k, {%6, %6};\n\t"
-      "add.rn.f32x2 t, x, k;\n\t"
-      "mov.b64 k, {%7, %7};\n\t"
-      "add.rn.f32x2 r, t, k;\n\t"
-      "sub.rn.f32x2 f, x, r;\n\t"
-      "mov.b64 k, {%8, %8};\n\t"
-      "mov.b64 p, {%9, %9};\n\t"
-      "fma.rn.f32x2 p, f, k, p;\n\t"
-      "mov.b64 k, {%10, %10};\n\t"
-      "fma.rn.f32x2 p, p, f, k;\n\t"
-      "mov.b64 k, {%11, %11};\n\t"
-      "fma.rn.f32x2 p, p, f, k;\n\t"
-      "mov.b64 {t0, t1}, t;\n\t"
-      "mov.b64 {p0, p1}, p;\n\t"
-      "max.s32 t0, t0, %12;\n\t"
-      "max.s32 t1, t1, %12;\n\t"
-      "shl.b32 t0, t0, 23;\n\t"
-      "shl.b32 t1, t1, 23;\n\t"
-      "add.s32 %0, p0, t0;\n\t"
-      "add.s32 %1, p1, t1;\n\t}"
-      : "=r"(r0), "=r"(r1)
-      : "r"(s0), "r"(s1), "f"(scale), "f"(nsub), "f"(12582912.0f), "f"(-12582912.0f), "f"(0.05517132207751274f),
-        "f"(0.24261054396629333f), "f"(0.6932609677314758f), "f"(0.9999281167984009f), "r"(0x4B400000 - 126));
-  e0 = __uint_as_float(r0);
-  e1 = __uint_as_float(r1);
-}
-
 struct Attn5Params {
   AttnOut out;
   int B, S, H, ctx_rows, ctx_keys, fp16;
@@ -238,8 +198,7 @@ struct Attn5Params {
   int rot;                 // per-round rotation of the item -> CTA map (load balance; see item_of)
 };
 
-// POLY: how many of the 16 score pairs a thread owns per tile take the polynomial exp2 (FMA pipe) instead of MUFU.EX2.
-template <bool FP16, int POLY>
+template <bool FP16>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
 attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -438,11 +397,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
       // Warp-uniform facts about this warp's 32 rows.  A quarter that lies entirely past the end of the sequence (the last
       // query tile of a ragged S: S runs from 276 to 768 over the sampler schedule) does no softmax work at all -- its P / O
-      // rows are never stored -- it only keeps pace with the barriers.  Unmasked tiles (every key visible to every row of
-      // the warp) may take the polynomial exp2 path, which needs finite inputs.
-      const int wrow0 = qt * BQ + quarter * 32;
-      const bool warp_valid = wrow0 < S;
-      const int kmax_w = (wrow0 < p.ctx_rows) ? p.ctx_keys : S;           // smallest key limit of the warp's rows
+      // rows are never stored -- it only keeps pace with the barriers.
+      const bool warp_valid = qt * BQ + quarter * 32 < S;
       float m_run = -INFINITY, l_part = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++g) {
         mbar_wait(s_full(g & 1), (g >> 1) & 1);
@@ -452,63 +408,84 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tmem_ld32(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, r0);
           tmem_ld_wait();
           const int k0 = j * BKV + 32 * half;
-          const bool masked_tile = k0 + 32 > kmax_w;                     // warp-uniform
           if (k0 + 32 > kmax) {                                           // tile straddles this row's key limit
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (k0 + i >= kmax) r0[i] = 0xff800000u;                    // -inf
           }
+          // P = 2^(s * scale - m) for this thread's 32 keys as 16 packed 16-bit columns + their fp32 sum.  Scale / subtract and
+          // the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2), ex2.approx on the MUFU pipe, one cvt per pair.
+          // With TRACK_MAX the half-row maximum of the raw scores is folded into the same loop (one 3-input max per pair), so
+          // that its instructions sit between the MUFU ops in program order and issue under their latency.
+          float mloc[4];
+          auto exps = [&](float nsub, uint32_t (&w)[16], auto track_max) -> float {
+            constexpr bool TRACK_MAX = decltype(track_max)::value;
+            float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+            if (TRACK_MAX) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) mloc[i] = -INFINITY;
+            }
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float x0, x1;
+              scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
+#ifdef SELFTOK_ABL_NO_EXP
+              const float e0 = x0, e1 = x1;
+#else
+              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+#endif
+              if (TRACK_MAX) mloc[q & 3] = fmaxf(mloc[q & 3], fmaxf(__uint_as_float(r0[2 * q]), __uint_as_float(r0[2 * q + 1])));
+              add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
+              w[q] = pack2_16(e0, e1, FP16);
+            }
+            return (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
+          };
+          // the half-row maxima of the two threads of a row meet in shared memory (double-buffered by tile parity: one
+          // 64-thread named barrier per tile)
+          auto exchange_max = [&](float mx) -> float {
+#ifdef SELFTOK_ABL_NO_MAX
+            return 0.f;
+#else
+            xch[((g & 1) * 2 + half) * BQ + rl] = mx;
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            return fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
+#endif
+          };
+          uint32_t w[16];
+          float rs = 0.f;
+          // SPECULATION: with the lazy rescale the reference maximum m_run almost never moves after the first tile of an item,
+          // so the exponentials are issued against m_run straight after the TMEM load, BEFORE the tile maximum is known; the
+          // max tree, the half-row exchange through shared memory and its named barrier then run under the MUFU latency
+          // instead of in front of it.  Only if some row of the warp did move its maximum (first tile; score jumps > 2^8)
+          // is the tile recomputed against the new maximum -- S is still in registers (P is stored after the check).
+#ifdef SELFTOK_ATTN_NO_SPEC
+          const bool spec = false;
+#else
+          const bool spec = j > 0 && __all_sync(0xffffffffu, m_run != -INFINITY);
+#endif
           float mx;
-          {
+          if (spec) {
+            rs = exps(-m_run, w, std::true_type());
+            mx = exchange_max(fmaxf(fmaxf(mloc[0], mloc[1]), fmaxf(mloc[2], mloc[3])));
+          } else {
             float mp[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
 #pragma unroll
             for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
-            mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+            mx = exchange_max(fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])));
           }
-          // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
-          xch[((g & 1) * 2 + half) * BQ + rl] = mx;
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-          mx = fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
           // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays
           // exact enough in 16 bits and the final O / l normalisation cancels the stale offset), so the O correction pass and
           // its wait on the previous P V are rare instead of per tile.  (-inf - -inf = NaN keeps m_run: comparison is false.)
           float m_new = fmaxf(m_run, mx * p.scale_log2e);
           if (m_new - m_run <= kRescaleThreshold) m_new = m_run;
-          const float sub = (m_new == -INFINITY) ? 0.f : m_new;
-          const float corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-          // scale / subtract and the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2).  The 32 exponentials of
-          // a thread are what bounds the kernel (16 MUFU lanes per SM and clock against 906 M scores per launch at S = 768), so
-          // POLY of the 16 pairs -- spread evenly, the two pipes run side by side -- evaluate 2^x on the FMA pipe instead.
-          uint32_t w[16];
-          float rsp[4] = {0.f, 0.f, 0.f, 0.f};
-          const float nsub = -sub;
-          if (POLY > 0 && !masked_tile) {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              float e0, e1;
-              if (((q * POLY) & 15) < POLY) {
-                exp2_poly2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, e0, e1);
-              } else {
-                float x0, x1;
-                scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
-                e0 = ex2_approx(x0); e1 = ex2_approx(x1);
-              }
-              add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
-              w[q] = pack2_16(e0, e1, FP16);
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              float x0, x1;
-              scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
-              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-              add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
-              w[q] = pack2_16(e0, e1, FP16);
-            }
+          float corr = 1.f;
+          if (!spec || __any_sync(0xffffffffu, m_new != m_run)) {
+            const float sub = (m_new == -INFINITY) ? 0.f : m_new;
+            corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
+            rs = exps(-sub, w, std::false_type());
           }
-          const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
           // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
           tmem_st16(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, w);
           l_part = l_part * corr + rs;
@@ -552,21 +529,6 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
-typedef void (*Attn5Fn)(const CUtensorMap, const CUtensorMap, const Attn5Params);
-// polynomial-exp2 pairs per thread and tile (of 16): the default balances the MUFU and FMA / issue budgets (see the kernel);
-// SELFTOK_ATTN_POLY = 0 | 4 | 5 | 6 | 8 selects another instantiation for A/B runs
-constexpr int kPolyDefault = 5;
-template <bool FP16>
-Attn5Fn attn5_fn(int poly) {
-  switch (poly) {
-    case 0: return attention_tc5_kernel<FP16, 0>;
-    case 4: return attention_tc5_kernel<FP16, 4>;
-    case 6: return attention_tc5_kernel<FP16, 6>;
-    case 8: return attention_tc5_kernel<FP16, 8>;
-    default: return attention_tc5_kernel<FP16, 5>;
-  }
-}
-int g_poly = -1;
 int g_num_sms_dev[64];
 bool g_attr_dev[64];       // cudaFuncSetAttribute is per device: one handle per GPU may live in the same process
 
@@ -574,28 +536,19 @@ int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 }  // namespace
 
-void attention_tc5_set_poly(int pairs) { g_poly = pairs; }
-
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16) {
   STK_CHECK(qkv16 && B > 0 && S > 0 && H > 0, -1, "attention_tc5: bad arguments");
   STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
   STK_CHECK(ctx_keys <= S && ctx_rows <= S, -1, "attention_tc5: context limits exceed the sequence");
   STK_TRY(gemm_tc_init());
-  if (g_poly < 0) {
-    const char* v = getenv("SELFTOK_ATTN_POLY");
-    g_poly = v ? atoi(v) : kPolyDefault;
-  }
   int dev = 0;
   STK_CUDA(cudaGetDevice(&dev));
   STK_CHECK(dev >= 0 && dev < 64, -1, "attention_tc5: device ordinal out of range");
-  Attn5Fn fn = fp16 ? attn5_fn<true>(g_poly) : attn5_fn<false>(g_poly);
   if (!g_attr_dev[dev]) {
     STK_CUDA(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
-    for (int pl : {0, 4, 5, 6, 8}) {
-      STK_CUDA(cudaFuncSetAttribute(attn5_fn<true>(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      STK_CUDA(cudaFuncSetAttribute(attn5_fn<false>(pl), cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    }
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_dev[dev] = true;
   }
   CUtensorMap mq, mkv;
@@ -608,7 +561,8 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   int rot = 0;                                                     // smallest rotation that makes the query-tile walk full-period
   while (gcd_i((grid + rot) % nq == 0 ? nq : (grid + rot) % nq, nq) != 1 && rot < nq) ++rot;
   Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f, rot};
-  fn<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  if (fp16) attention_tc5_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  else attention_tc5_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

@@ -980,13 +980,6 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_set_gemm_ctas(in
   return SELFTOK_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int selftok_k_set_attn_poly(int pairs) {
-  STK_CHECK(pairs == 0 || pairs == 4 || pairs == 5 || pairs == 6 || pairs == 8, SELFTOK_ERR_BAD_ARG,
-            "selftok_k_set_attn_poly: pairs must be 0, 4, 5, 6 or 8");
-  attention_tc5_set_poly(pairs);
-  return SELFTOK_OK;
-}
-
 extern "C" __attribute__((visibility("default"))) int selftok_k_ln_mod_f32(const float* x, const float* shift, const float* scale, int64_t ld_mod, int period,
                                     float* out, int64_t M, int D, void* stream) {
   return launch_ln_mod(x, D, shift, scale, ld_mod, period, out, nullptr, nullptr, D, M, D, 1e-6f, (cudaStream_t)stream);

@@ -110,7 +110,6 @@ int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo
                         int ctx_rows, int ctx_keys, const AttnOut& out, cudaStream_t s, int fp16 = 0);
 
 // tcgen05 / TMEM attention (attn_tc5.cu), single-pass 16-bit operands (fp16 != 0: IEEE half, else bf16)
-void attention_tc5_set_poly(int pairs);   // 0 | 4 | 5 | 6 | 8 polynomial-exp2 pairs of 16 (A/B switch)
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16);
 

@@ -153,6 +153,79 @@ def synth_state_dict(d: SelftokDims, seed: int = 0, device="cpu", include_aux: b
     return sd
 
 
+# ---------------------------------------------------------------------------------------------- SD3 VAE (16 channels)
+def vae_state_dict_spec(ch: int = 128, ch_mult=(1, 2, 4, 4), num_res_blocks: int = 2, z_channels: int = 16,
+                        decoder: bool = True, encoder: bool = True) -> "OrderedDict[str, Tuple[Tuple[int, ...], str, float]]":
+    """Tensors of the SD3 VAE under the in-tree `SDVAE` key names (sd3/sd3_impls.py:221-474): GroupNorm(32) + SiLU +
+    3x3 convolutions, one single-head attention block in the middle.  ch = 128 is the released architecture."""
+    s: "OrderedDict[str, Tuple[Tuple[int, ...], str, float]]" = OrderedDict()
+
+    def conv(prefix, cout, cin, k, gain=1.4):
+        s[prefix + ".weight"] = ((cout, cin, k, k), "w", gain / math.sqrt(cin * k * k))
+        s[prefix + ".bias"] = ((cout,), "b", 0.02)
+
+    def norm(prefix, c):
+        s[prefix + ".weight"] = ((c,), "ln_w", 0.05)
+        s[prefix + ".bias"] = ((c,), "ln_b", 0.05)
+
+    def resnet(prefix, cin, cout):
+        norm(prefix + ".norm1", cin)
+        conv(prefix + ".conv1", cout, cin, 3)
+        norm(prefix + ".norm2", cout)
+        conv(prefix + ".conv2", cout, cout, 3, gain=0.7)
+        if cin != cout:
+            conv(prefix + ".nin_shortcut", cout, cin, 1, gain=1.0)
+
+    def attn(prefix, c):
+        norm(prefix + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            conv(prefix + "." + n, c, c, 1, gain=1.0)
+
+    nres = len(ch_mult)
+    if encoder:
+        p = "encoder."
+        conv(p + "conv_in", ch, 3, 3, gain=1.0)
+        in_mult = (1,) + tuple(ch_mult)
+        cin = ch
+        for lvl in range(nres):
+            cin, cout = ch * in_mult[lvl], ch * ch_mult[lvl]
+            for b in range(num_res_blocks):
+                resnet(f"{p}down.{lvl}.block.{b}", cin, cout)
+                cin = cout
+            if lvl != nres - 1:
+                conv(f"{p}down.{lvl}.downsample.conv", cin, cin, 3, gain=1.0)
+        resnet(p + "mid.block_1", cin, cin)
+        attn(p + "mid.attn_1", cin)
+        resnet(p + "mid.block_2", cin, cin)
+        norm(p + "norm_out", cin)
+        conv(p + "conv_out", 2 * z_channels, cin, 3)
+    if decoder:
+        p = "decoder."
+        cin = ch * ch_mult[-1]
+        conv(p + "conv_in", cin, z_channels, 3, gain=1.0)
+        resnet(p + "mid.block_1", cin, cin)
+        attn(p + "mid.attn_1", cin)
+        resnet(p + "mid.block_2", cin, cin)
+        for lvl in reversed(range(nres)):
+            cout = ch * ch_mult[lvl]
+            for b in range(num_res_blocks + 1):
+                resnet(f"{p}up.{lvl}.block.{b}", cin, cout)
+                cin = cout
+            if lvl != 0:
+                conv(f"{p}up.{lvl}.upsample.conv", cin, cin, 3, gain=1.0)
+        norm(p + "norm_out", cin)
+        conv(p + "conv_out", 3, cin, 3, gain=0.6)
+    return s
+
+
+def synth_vae_state_dict(ch: int = 128, seed: int = 0, device="cpu", **kw) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic VAE checkpoint (same integer-hash generator as the tokenizer's): bit-identical on any host."""
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    for name, (shape, kind, std) in vae_state_dict_spec(ch, **kw).items():
+        sd[name] = synth_tensor("vae." + name, shape, kind, std, seed, device)
+    return sd
+
+
 def num_params(d: SelftokDims) -> int:
     n = 0
     for shape, _, _ in state_dict_spec(d).values():
