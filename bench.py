@@ -16,6 +16,11 @@ Printed JSON (rank 0, one line): metric/value/unit/... per the driver contract, 
   roofline     tcgen05 GEMM class (dominant kernel): algorithmic FLOPs / summed CUDA-event time of its launches in one
                profiled step, against MEASURED_PEAKS.json's sustained bf16 GEMM rate
   cpu_baseline oracle port of the reference arithmetic (torch fp32 on the host cores) on a bounded sample
+  extra        (N = 1 only) sub-records for the other BASELINE configs, each measured in this run:
+                 config2_encode_only   batch-64 encode img/s + the fused VQ kernel alone (ms, algorithmic GB/s vs HBM peak,
+                                       fp32 TFLOP/s vs the FFMA peak -- the pipe that actually bounds it)
+                 config3_bf16x3        the headline workload in the fp32-faithful split-bf16 mode
+                 config4_renderer_512 / _1024   batch-64 encode + ONE renderer pass (img/s), 512 and 1024 tokens
 """
 from __future__ import annotations
 
@@ -91,6 +96,17 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def gemm_traffic():
+    """DRAM bytes per tcgen05 GEMM launch: NOT measured by this run (ncu cannot run inside a timed bench) -- read from the
+    committed extract of the round's `ncu --set full` capture of one MMDiT layer (profiles/extract_ncu.py)."""
+    for name in ("r2_gemm_traffic.json", "r1_gemm_traffic.json"):
+        p = os.path.join(REPO, "profiles", name)
+        if os.path.exists(p):
+            d = json.load(open(p))
+            return {"bytes_per_launch": float(d["bytes_per_launch"]), "source": f"profiles/{name}: " + d["source"]}
+    return {"bytes_per_launch": None, "source": "no committed ncu extract"}
+
+
 def gemm_flops_per_step(B: int) -> float:
     """Algorithmic (single-product, masked-effective) FLOPs of the tcgen05 GEMM launches of one 50-step decode:
     per layer and stream qkv 2*M*D*3D, proj 2*M*D*D, fc1+fc2 16*M*D*D; the last layer's context stream is qkv only."""
@@ -107,50 +123,65 @@ def gemm_flops_per_step(B: int) -> float:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(n_threads=None):
-    """Bounded sample of the reference arithmetic on the host: B=1 full-geometry encode + the first decode step
-    (k = 511, all tokens visible), including the reference's per-step dead encoder+VQ call (rectified_flow.py:212-215).
-    Extrapolated to 50 steps with the per-step FLOP model; returns images/s and the sample description."""
+def cpu_sample(n_threads=None, batches=(1,)):
+    """Bounded sample of the reference arithmetic on the host: full-geometry encode + the first decode step (k = 511, all
+    tokens visible), including the reference's per-step dead encoder+VQ call (rectified_flow.py:212-215), at batch sizes
+    `batches`.  Extrapolated to 50 steps with the per-step FLOP model.  Returns (one(B) -> (t_enc, t_step), scale).
+
+    "All the host threads it can use": torch's CPU GEMMs stop scaling (and regress) well below the core count of a 100+-core
+    host, so the thread count is calibrated ON THE DECODE STEP (98 % of the CPU time) and the fastest setting is used; a B = 1
+    step is M-starved (768 GEMM rows), which is why B = 4 is timed next to it."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     import selftok_oracle as O
     d = C.FULL
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     sd = {k: v.cpu() for k, v in synth.synth_state_dict(d, device=dev).items()}
     tb = S.make_tables(d.K, d.stages, d.k_per_stage, DECODE_STEPS)
-    x0 = synth.synth_tensor("bench.cpu.x0", (1, d.in_channels, d.latent, d.latent), "emb", 1.0)
-    noise = synth.synth_tensor("bench.cpu.noise", (1, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    Bmax = max(batches)
+    x0 = synth.synth_tensor("bench.cpu.x0", (Bmax, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    noise = synth.synth_tensor("bench.cpu.noise", (Bmax, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    state = {}
 
-    def one():
+    def one(B=1):
         t0 = time.perf_counter()
         with torch.no_grad():
-            outs_q, tok, _ = O.encode(sd, d, x0, tb)
+            outs_q, tok, _ = O.encode(sd, d, x0[:B], tb)
             t1 = time.perf_counter()
-            O.decode(sd, d, tok, noise, steps=DECODE_STEPS, tables=tb, n_steps_run=1, replay_dead_encoder_call=True)
+            O.decode(sd, d, tok, noise[:B], steps=DECODE_STEPS, tables=tb, n_steps_run=1, replay_dead_encoder_call=True)
         t2 = time.perf_counter()
+        state["tok"] = tok
         return t1 - t0, t2 - t1
 
-    # "all the host threads it can use": torch's CPU GEMMs stop scaling (and regress) well below the core count of a
-    # 100+-core host, so the thread count is calibrated on the encode leg (~1 s) and the fastest setting is used.
     cores = n_threads or os.cpu_count() or 1
     with torch.no_grad():
-        O.encode(sd, d, x0, tb)                       # first-call overheads (thread pool, primitive caches) excluded
+        one(1)                                        # first-call overheads (thread pool, primitive caches) excluded
         best_n, best_t = None, None
         for n in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
             torch.set_num_threads(n)
-            O.encode(sd, d, x0, tb)
-            t0 = time.perf_counter()
-            O.encode(sd, d, x0, tb)
-            t = time.perf_counter() - t0
+            t = one(1)[1]
             if best_t is None or t < best_t:
                 best_n, best_t = n, t
         torch.set_num_threads(best_n)
 
-    eff = []
     D, N, L = d.dit_hidden, d.n_img, d.dit_depth
+    eff = []
     for i in range(DECODE_STEPS):       # the reference computes the DENSE K+N sequence every step (masked, not dropped)
         eff.append(sum(S.dense_flops_per_image_step(D, d.K, N, j == L - 1) for j in range(L)))
     scale = sum(eff) / eff[0]
     return one, scale
+
+
+def cpu_record(one, scale, batches=(1, 4)):
+    best, parts = None, []
+    for B in batches:
+        t_enc, t_step = one(B)
+        v = B / (t_enc + t_step * scale)
+        parts.append(f"B={B}: encode {t_enc:.2f}s + decode step 0 incl. the reference's dead encoder call {t_step:.2f}s -> {v:.4f} img/s")
+        if best is None or v > best:
+            best = v
+    sample = ("full-geometry encode + first decode step, x%.1f (dense per-step FLOP model) for 50 steps, extrapolated; thread count "
+              "calibrated on the decode step; " % scale) + "; ".join(parts)
+    return {"value": best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample}
 
 
 def run_reference(args):
@@ -159,32 +190,108 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    one, scale = cpu_sample(cores)
+    one, scale = cpu_sample(cores, batches=(1, 4))
     for _ in range(args.warmup):
-        one()
-    t_enc = t_step = 0.0
+        one(1)
     t0 = time.perf_counter()
+    rec = None
     for _ in range(args.steps):
-        a, b = one()
-        t_enc += a
-        t_step += b
+        r = cpu_record(one, scale, batches=(1, 4))
+        if rec is None or r["value"] > rec["value"]:
+            rec = r
     wall = time.perf_counter() - t0
-    t_enc /= args.steps
-    t_step /= args.steps
-    img_s = 1.0 / (t_enc + t_step * scale)
-    sample = (f"B=1 full-geometry encode ({t_enc:.2f}s) + decode step 0 incl. the reference's dead encoder call ({t_step:.2f}s), "
-              f"x{scale:.1f} (dense per-step FLOP model) for 50 steps; extrapolated")
+    img_s = rec["value"]
     line = {"impl": "reference", "metric": METRIC, "value": img_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "B=1 256x256 encode + 50-step decode, 512 tokens (bounded sample per step)", "batch_per_gpu": 1},
-            "cpu_baseline": {"value": img_s, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "config": {"workload": "256x256 encode + 50-step decode, 512 tokens (bounded sample per step: B=1 and B=4, best of the two)",
+                       "batch_per_gpu": 1},
+            "cpu_baseline": rec,
             "e2e": {"value": img_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def run_extras(args, eng, dev, x0, noise, timed):
+    """Sub-records for BASELINE configs 2 and 4 and the fp32-faithful mode (see the module docstring).  `eng` is the
+    headline engine (still alive); every other engine is created here and closed before the next one."""
+    from selftoktokenizer_b200.capi import Engine
+    import dataclasses
+    d = C.FULL
+    B = x0.shape[0]
+    pk = peaks()
+    out = {}
+    # ---- config 2: encode only + the fused VQ kernel alone
+    def enc_only():
+        eng.encode(x0)
+    enc_only()
+    ms, _ = timed(enc_only, 5)
+    tok, outs_q, feats = eng.encode(x0, return_aux=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ts = []
+    for _ in range(13):
+        flush.zero_()                                         # L2 flushed between iterations (256 MiB > 126 MB)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.vq_argmax(feats)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    vq_ms = sorted(ts[3:])[len(ts[3:]) // 2]
+    R = B * d.K
+    vq_bytes = R * d.enc_qdim * 4 + d.codebook_size * d.code_dim * 4 + d.code_dim * d.enc_qdim * 4 + R * 8 + R * d.code_dim * 4
+    vq_flops = 2.0 * R * d.codebook_size * d.code_dim + 2.0 * R * d.enc_qdim * d.code_dim
+    ffma_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    out["config2_encode_only"] = {
+        "workload": f"batch={B} 256x256 encode only (16-block Q-Former + fused VQ -> 512 tokens)", "value": B * 5 / (ms / 1000.0), "unit": UNIT,
+        "ms_per_batch": ms / 5,
+        "vq_kernel": {"ms": vq_ms, "algorithmic_bytes": vq_bytes, "achieved_GBps": vq_bytes / vq_ms / 1e6, "hbm_peak_GBps": pk["hbm"],
+                      "frac_hbm": vq_bytes / vq_ms / 1e6 / pk["hbm"], "achieved_fp32_TFLOPs": vq_flops / vq_ms / 1e9,
+                      "fp32_ffma_peak_TFLOPs_nominal": ffma_peak, "frac_ffma": vq_flops / vq_ms / 1e9 / ffma_peak,
+                      "bound": "fp32 FFMA pipe (35.5 GFLOP on 71.6 MB: 11 us of HBM time); the HBM fraction is reported because the "
+                               "north-star asks for it (SURVEY 8d)", "timing": "median of 10, CUDA events, L2 flushed"}}
+    del flush
+    # ---- config 3 in the fp32-faithful mode
+    if args.precision != "bf16x3":
+        e3 = Engine(d, synth.synth_state_dict(d, device=dev), device=dev, precision="bf16x3", steps=DECODE_STEPS)
+
+        def step3():
+            t = e3.encode(x0)
+            e3.decode(t, noise)
+        step3()
+        ms3, _ = timed(step3, 1)
+        out["config3_bf16x3"] = {"workload": f"batch={B} encode + 50-step decode, split-bf16 (3 MMAs / product) GEMMs and attention",
+                                 "value": B / (ms3 / 1000.0), "unit": UNIT, "ms_per_step": ms3}
+        e3.close()
+        del e3
+        torch.cuda.empty_cache()
+    # ---- config 4: encode + one renderer pass, 512 and 1024 tokens
+    for K, kps in ((512, (512,)), (1024, (1024,))):
+        dr = dataclasses.replace(d, K=K, stages=(1000,), k_per_stage=kps, renderer=True)
+        er = Engine(dr, synth.synth_state_dict(dr, device=dev), device=dev, precision="auto")
+
+        def step4():
+            t = er.encode(x0)
+            er.render(t)
+        step4()
+        ms4, _ = timed(step4, 3)
+        flops = None
+        try:
+            D_, N_, L_ = dr.dit_hidden, dr.n_img, dr.dit_depth
+            flops = sum(S.dense_flops_per_image_step(D_, K, N_, j == L_ - 1) for j in range(L_))
+        except Exception:
+            pass
+        out[f"config4_renderer_{K}"] = {"workload": f"batch={B} 256x256 encode ({K} tokens) + ONE MMDiT_Renderer pass, no VAE",
+                                        "value": B * 3 / (ms4 / 1000.0), "unit": UNIT, "ms_per_batch": ms4 / 3, "precision": er.precision,
+                                        "renderer_dense_tflop_per_image": None if flops is None else flops / 1e12}
+        er.close()
+        del er
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from selftoktokenizer_b200.capi import Engine
@@ -270,6 +377,7 @@ def run_gpu(args):
         eng.set_profile(False)
         eng.set_use_graph(True)
         pk = peaks()
+        traffic = gemm_traffic()
         total_ms = sum(v[0] for v in prof.values())
         if "gemm_tcgen05" in prof:
             g_ms, g_n = prof["gemm_tcgen05"]
@@ -277,24 +385,24 @@ def run_gpu(args):
             ach = flops / (g_ms / 1000.0) / 1e12
             roof = {"bound": "tensor", "kernel": "gemm_tc2_kernel (tcgen05 cta_group::2 kind::f16, %s)" % args.precision,
                     "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                    "traffic": 0.906e9 if B == BATCH else None, "traffic_unit": "bytes/launch",
-                    "traffic_source": "ncu dram__bytes_read+write of the 4 grouped GEMM launches of one layer at step 0 (3.63 GB with the "
-                                      "evict_last hint on the weight tiles; 4.05 GB without), per launch; profiles/r1_layer_ncu_full_final.md; "
-                                      "algorithmic operand+output bytes 3.38 GB per layer",
+                    "traffic": traffic["bytes_per_launch"] if B == BATCH else None, "traffic_unit": "bytes/launch",
+                    "traffic_source": traffic["source"],
+                    "timed_in": "a separate graph-off pass of the same step with CUDA events around every launch (the timed region replays "
+                                "one CUDA graph; class shares of the two agree within 1 %)",
                     "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,
                     "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs)"}
+    # ---- the other BASELINE configs, measured in the same run (N = 1 only; each engine is built, timed and released)
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = run_extras(args, eng, dev, x0, noise, timed)
     # ---- CPU baseline (oracle port on the host cores), rank 0 at N=1 only
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         eng.close()
         torch.cuda.empty_cache()
-        one, scale = cpu_sample(os.cpu_count())
-        t_enc, t_step = one()
-        v = 1.0 / (t_enc + t_step * scale)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"B=1 full-geometry encode ({t_enc:.2f}s) + decode step 0 incl. the reference's dead encoder call "
-                         f"({t_step:.2f}s), x{scale:.1f} dense per-step FLOP model for 50 steps; extrapolated"}
+        one, scale = cpu_sample(os.cpu_count(), batches=(1, 4))
+        cpu = cpu_record(one, scale, batches=(1, 4))
     if rank == 0:
         eff, dense = S.decode_flops_per_image(d.K, d.stages, d.k_per_stage, DECODE_STEPS, d.dit_depth, d.n_img)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -306,11 +414,12 @@ def run_gpu(args):
                 "config": {"workload": f"batch={B}/GPU 256x256 encode + 50-step diffusion decode (512 tokens, no VAE/renderer)",
                            "batch_per_gpu": B, "global_batch": B * world, "decode_steps": DECODE_STEPS, "precision": args.precision,
                            "parallelism": f"dp{world} (images sharded, weights replicated, 1 NCCL all-gather of tokens/step)",
-                           "l2": "working set >> L2: 16.7 GB of weight planes + ~3 GB activations streamed per DiT step",
+                           "l2": "working set >> L2 (126 MB): %.1f GB of 16-bit weight planes + ~3 GB of activations streamed per DiT step"
+                                 % (4.17 * (2 if args.precision == "bf16x3" else 1)),
                            "algorithmic_tflop_per_image": eff / 1e12},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_h / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra,
                 "kernel_classes_ms": {k: round(v[0], 3) for k, v in prof.items()},
                 "kernel_classes_launches": {k: v[1] for k, v in prof.items()}}
         print(json.dumps(line), flush=True)
@@ -327,6 +436,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("SELFTOK_PRECISION", "fp16"), choices=["bf16x3", "fp16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-records of the other BASELINE configs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -133,6 +133,12 @@ int selftok_decode_host(selftok_handle_t h, const int64_t* tokens_host, const fl
                         float* x0_out_host, void* stream);
 int selftok_render_host(selftok_handle_t h, const int64_t* tokens_host, int B, float* x0_out_host, void* stream);
 
+/* Token ids outside [0, codebook_size) are an error, as `codebook[idx]` is in the reference: the lookup poisons the row
+ * with NaN (so everything derived from it is NaN) and counts it.  The *_host entry points return SELFTOK_ERR_BAD_ARG;
+ * after a device-buffer call, selftok_id_errors synchronises `stream`, returns the count since the last query and
+ * resets it (< 0: CUDA error). */
+int64_t selftok_id_errors(selftok_handle_t h, void* stream);
+
 /* ---- introspection ----------------------------------------------------------------------------------------- */
 /* Number of kernel launches issued (or replayed from a graph) by the last hot-path call on this handle. */
 int64_t selftok_last_launch_count(selftok_handle_t h);

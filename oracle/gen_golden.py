@@ -210,6 +210,27 @@ def gen_tiny():
           float((tokens[0] != tokens[1]).float().mean()))
 
 
+def gen_mid(stress=False):
+    """Mid-size geometry, B = 4 (B >= 4 on a reduced-depth config).  stress=True: the same run on the
+    heavy-tailed / outlier-channel checkpoint (synth._stress) -- the fp16-operand stress fixture."""
+    dims = C.MID
+    ref_loader.import_reference()
+    sd = synth.synth_state_dict(dims, stress=stress)
+    enc_name, dit_name = ref_loader.register_geometry(dims, "midstress" if stress else "mid")
+    cfg = ref_loader.dims_to_cfg(dims, enc_name, dit_name)
+    pipe = ref_loader.build_reference_pipeline(cfg, sd)
+    B = 4
+    x0 = latents("golden.mid.x0", B, dims)
+    outs_q, tokens, z, margin = ref_encode(pipe, x0)
+    t0 = time.time()
+    noise, pred_x0 = ref_decode(pipe, tokens.numpy(), seed=4321)
+    print(f"mid{'_stress' if stress else ''}: decode B={B} in {time.time() - t0:.1f}s; |pred_x0|max {float(pred_x0.abs().max()):.2f}; "
+          f"min margin {float(margin.min()):.2e}", flush=True)
+    v0 = ref_velocity(pipe, noise, 0, outs_q)
+    v49 = ref_velocity(pipe, noise, 49, outs_q)
+    save("mid_stress" if stress else "mid", tokens=tokens, margin=margin, noise=noise, pred_x0=pred_x0, v0=v0, v49=v49)
+
+
 def gen_tiny_renderer():
     dims = TINY_R
     pipe, _ = build(dims, tag="tinyr")
@@ -279,6 +300,41 @@ def gen_full_renderer():
     save("full_renderer", pred_x0=pred_x0)
 
 
+def gen_full_renderer_1024():
+    """BASELINE config 4: one renderer pass with 1024 tokens at the full geometry (README.md:93-94; the reference ships no
+    YAML for it -- configs/selftok_renderer_1024tok.yml = the 512-token renderer YAML with k doubled), B = 1."""
+    dims = C.dataclasses.replace(C.FULL, K=1024, stages=(1000,), k_per_stage=(1024,), renderer=True)
+    ref_loader.import_reference()
+    sd = synth.synth_state_dict(dims)
+    cfg = ref_loader.dims_to_cfg(dims)
+    cfg.tokenizer.params.stages, cfg.tokenizer.params.k_per_stage = "1000", "1024"
+    pipe = ref_loader.build_reference_pipeline(cfg, sd)
+    tokens = (synth.synth_tensor("golden.r1024.tokens", (1, dims.K), "emb", 1.0) + 0.5).mul(dims.codebook_size).long().clamp(0, dims.codebook_size - 1)
+    outs_q = lookup(pipe, tokens)
+    t0 = time.time()
+    with torch.no_grad():
+        pred_x0, _ = pipe.model.model(y=None, encoder_hidden_states=outs_q)
+    print(f"renderer K=1024 B=1: {time.time() - t0:.1f}s")
+    save("full_renderer_1024", tokens=tokens, pred_x0=pred_x0)
+
+
+def gen_tiny_datasize():
+    """Non-default `datasize` (the reference's CLI argument): the TINY checkpoint (image_size 64) run at datasize 96 --
+    latent 12, encoder and decoder positional grids centre-cropped to 6 x 6 (models_ours.py:183-202, sd3/mmdit.py:877-896)."""
+    dims = C.TINY
+    ref_loader.import_reference()
+    sd = synth.synth_state_dict(dims)
+    enc_name, dit_name = ref_loader.register_geometry(dims, "tinyds")
+    cfg = ref_loader.dims_to_cfg(dims, enc_name, dit_name)
+    pipe = ref_loader.build_reference_pipeline(cfg, sd, datasize=96)
+    d96 = C.dataclasses.replace(dims, latent=12)
+    x0 = latents("golden.tinyds.x0", 2, d96)
+    outs_q, tokens, z, margin = ref_encode(pipe, x0)
+    noise, pred_x0 = ref_decode(pipe, tokens.numpy(), seed=99)
+    assert tuple(noise.shape) == (2, 16, 12, 12)
+    save("tiny_ds96", tokens=tokens, margin=margin, noise=noise, pred_x0=pred_x0)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["tiny"]
     pipe = None
@@ -295,6 +351,14 @@ if __name__ == "__main__":
             gen_full_decode(pipe)
         elif w == "full_renderer":
             gen_full_renderer()
+        elif w == "mid":
+            gen_mid(False)
+        elif w == "mid_stress":
+            gen_mid(True)
+        elif w == "full_renderer_1024":
+            gen_full_renderer_1024()
+        elif w == "tiny_ds96":
+            gen_tiny_datasize()
         elif w == "vae_tiny":
             gen_vae_tiny()
         elif w == "tiny_pixels":

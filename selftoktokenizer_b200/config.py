@@ -120,34 +120,43 @@ class SelftokDims:
         return (self.latent // self.enc_patch) ** 2
 
     def validate(self) -> None:
-        assert self.enc_hidden % self.enc_heads == 0 and self.enc_qdim % self.enc_qheads == 0
-        assert self.latent % self.enc_patch == 0 and self.latent % self.dit_patch == 0
-        assert sum(self.k_per_stage) == self.K, "k_per_stage must sum to K"
-        assert len(self.stages) == len(self.k_per_stage)
-        assert self.latent // self.enc_patch <= self.enc_pos_max
-        assert self.latent // self.dit_patch <= self.dit_pos_max
+        """Raises ValueError (never a bare assert: the checks must survive `python -O`)."""
+        def need(cond, msg):
+            if not cond:
+                raise ValueError("SelftokDims: " + msg)
+        need(self.enc_hidden % self.enc_heads == 0 and self.enc_qdim % self.enc_qheads == 0, "hidden sizes must divide into heads")
+        need(self.latent % self.enc_patch == 0 and self.latent % self.dit_patch == 0, "latent side must be a multiple of the patch size")
+        need(sum(self.k_per_stage) == self.K, "k_per_stage must sum to K")
+        need(len(self.stages) == len(self.k_per_stage), "stages and k_per_stage must have the same length")
+        need(self.latent // self.enc_patch <= self.enc_pos_max, "encoder positional grid smaller than the latent grid")
+        need(self.latent // self.dit_patch <= self.dit_pos_max, "decoder positional grid smaller than the latent grid")
 
     @staticmethod
     def from_cfg(cfg: Mapping, datasize: Optional[int] = None) -> "SelftokDims":
         """Flatten ``cfg.tokenizer.params`` exactly as ImageTokenizer.__init__ consumes it
         (image_tokenizer.py:85-147).  Does NOT mutate cfg (the reference does: SelftokPipeline.py:166,
-        image_tokenizer.py:88-92 — documented quirk, consciously dropped)."""
+        image_tokenizer.py:88-92 — documented quirk, consciously dropped).  Unsupported settings raise ValueError / KeyError
+        (registry lookups), as the reference's constructors would fail."""
+        def need(cond, msg):
+            if not cond:
+                raise ValueError("selftok config: " + msg)
         p = cfg["tokenizer"]["params"]
         enc = ENC_MODELS[p["enc"]]
         dit = DIT_MODELS[p["model"]]
-        assert p.get("diffusion_type", "flow") == "flow"
+        need(p.get("diffusion_type", "flow") == "flow", "only diffusion_type 'flow' is on the shipped path")
         image_size = int(datasize or p["image_size"])
-        assert image_size % 8 == 0, "Image size must be divisible by 8 (for the VAE encoder)."
+        need(image_size % 8 == 0, "Image size must be divisible by 8 (for the VAE encoder).")
         latent = image_size // 8
         ec = p.get("encoder_config", {})
-        assert ec.get("qformer_mode", "dual") == "dual", "only the 'dual' Q-Former mode is on the shipped path"
-        assert ec.get("time_adaln", True) and not ec.get("attn_mask", False) and not ec.get("qk_norm", False)
-        assert ec.get("post_norm", True) and not ec.get("pre_norm", False)
+        need(ec.get("qformer_mode", "dual") == "dual", "only the 'dual' Q-Former mode is on the shipped path")
+        need(ec.get("time_adaln", True) and not ec.get("attn_mask", False) and not ec.get("qk_norm", False),
+             "encoder_config must be time_adaln, no attn_mask, no qk_norm")
+        need(ec.get("post_norm", True) and not ec.get("pre_norm", False), "encoder_config must be post_norm")
         qc = p["quantizer_config"]
-        assert not qc.get("continuous", False)
-        assert int(qc["code_dim"]) == int(p["encoder_hidden_size"]), "project_out must be Identity"
+        need(not qc.get("continuous", False), "continuous quantizer is not on the shipped path")
+        need(int(qc["code_dim"]) == int(p["encoder_hidden_size"]), "project_out must be Identity (code_dim == encoder_hidden_size)")
         dc = p.get("decoder_config", {})
-        assert dc.get("time_adaln", "pos_emb") == "pos_emb"
+        need(dc.get("time_adaln", "pos_emb") == "pos_emb", "decoder_config.time_adaln must be 'pos_emb'")
         d = SelftokDims(
             K=int(p["k"]), stages=_parse_int_list(p["stages"]), k_per_stage=_parse_int_list(p["k_per_stage"]),
             latent=latent, in_channels=int(p.get("in_channels", 16)),
@@ -170,5 +179,14 @@ TINY = SelftokDims(
     enc_patch=2, enc_hidden=64, enc_heads=4, enc_depth=2, enc_qdim=128, enc_qheads=2, enc_pos_max=16,
     codebook_size=1024, code_dim=16,
     dit_depth=3, dit_patch=2, dit_pos_max=12, renderer=False, context_see_xt=True,
+)
+# A mid-size geometry (multi-tile everywhere: S up to 192 joint rows, 6 heads, 4096 codes) for batched fixtures the CPU
+# reference still finishes in seconds: B >= 4 decode and the fp16 outlier-weight stress fixture.
+MID = SelftokDims(
+    K=128, stages=(200, 400, 600, 800, 1000), k_per_stage=(48, 46, 18, 12, 4),
+    latent=16, in_channels=16,
+    enc_patch=2, enc_hidden=64, enc_heads=4, enc_depth=4, enc_qdim=256, enc_qheads=4, enc_pos_max=32,
+    codebook_size=4096, code_dim=16,
+    dit_depth=6, dit_patch=2, dit_pos_max=24, renderer=False, context_see_xt=True,
 )
 FULL = SelftokDims()

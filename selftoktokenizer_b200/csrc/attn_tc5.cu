@@ -191,6 +191,22 @@ __device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
   return r;
 }
 
+#ifdef SELFTOK_ATTN_TRACE
+// debug build only (profiles/mk_variant.sh with -DSELFTOK_ATTN_TRACE): per-event clock stamps of CTA 0, one private slot
+// list per warp (plain stores, no atomics: a returning atomic would put ~1000 cycles of latency into every stamp)
+__device__ unsigned long long g_trace[16][4096];
+#define TRACE_DECL int trace_i = 0
+#define TRACE(tag, g)                                                                                                   \
+  do {                                                                                                                  \
+    if (lane == 0 && blockIdx.x == 0 && trace_i < 4096)                                                                 \
+      g_trace[warp][trace_i++] = ((unsigned long long)(tag) << 56) | ((unsigned long long)(warp & 0xff) << 48) |        \
+                                 ((unsigned long long)((g) & 0xffff) << 32) | (unsigned long long)(clock64() & 0xffffffffu); \
+  } while (0)
+#else
+#define TRACE_DECL
+#define TRACE(tag, g) do { } while (0)
+#endif
+
 struct Attn5Params {
   AttnOut out;
   int B, S, H, ctx_rows, ctx_keys, fp16;
@@ -219,6 +235,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TRACE_DECL;
   const int S = p.S;
   // persistent CTA: work items (image b, head h, query tile qt), qt fastest, so that the CTAs running side by side share
   // the K / V tiles of one (b, h) in L2.  All roles walk the same item sequence with a CTA-global tile counter g that
@@ -307,6 +324,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tc_mma_f16(s_tmem0 + 64 * (gg & 1), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
         tc_commit(s_full(gg & 1));
         if (last) tc_commit(q_empty(qb));
+        TRACE(12, gg);
       };
       int g = 0, n = 0;
       if (item_of(0) >= 0) {
@@ -323,6 +341,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const int st = g % KV_STAGES;
           const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
           mbar_wait(p_ready(g & 1), (g >> 1) & 1);                       // P_g in TMEM, O rescaled (or read out), S[g & 1] consumed
+          TRACE(10, g);
           tc_fence_after();
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)                             // K dimension = keys: 16 keys = 2 atoms of 8 key rows
@@ -330,6 +349,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
                           idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
           tc_commit(kv_empty(st));                                       // K/V stage reusable once QK_g and PV_g retire
           tc_commit(pv_done(g & 1));                                     // O[n & 1] holds tiles 0..j of the item
+          TRACE(11, g);
         }
       }
     }
@@ -402,11 +422,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       float m_run = -INFINITY, l_part = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++g) {
         mbar_wait(s_full(g & 1), (g >> 1) & 1);
+        TRACE(1, g);
         if (warp_valid) {
           tc_fence_after();
           uint32_t r0[32];
           tmem_ld32(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, r0);
           tmem_ld_wait();
+          TRACE(2, g);
           const int k0 = j * BKV + 32 * half;
           if (k0 + 32 > kmax) {                                           // tile straddles this row's key limit
 #pragma unroll
@@ -486,6 +508,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
             rs = exps(-sub, w, std::false_type());
           }
+          TRACE(3, g);
           // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
           tmem_st16(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, w);
           l_part = l_part * corr + rs;
@@ -501,6 +524,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             tmem_st32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
           }
           tmem_st_wait();                                                   // P (and the rescaled O) are in TMEM
+          TRACE(4, g);
         }
         tc_fence_before();
         __syncwarp();
@@ -567,5 +591,16 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   STK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#ifdef SELFTOK_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int selftok_dbg_attn_trace(unsigned long long* out_host, int max_n) {
+  cudaDeviceSynchronize();
+  if (max_n < 16 * 4096) return -1;
+  cudaMemcpyFromSymbol(out_host, g_trace, sizeof(unsigned long long) * 16 * 4096);
+  static unsigned long long zeros[16 * 4096];
+  cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
+  return 16 * 4096;
+}
+#endif
 
 }  // namespace stk

@@ -61,6 +61,7 @@ struct selftok_engine {
   bool finalized = false;
   bool use_graph = true;
   bool attn_tcgen05 = true;             // single-pass modes: tcgen05/TMEM attention (SELFTOK_ATTN=mma selects the mma.sync kernel)
+  int attn_gen = 6;                     // 6: four-stream kernel (attn_tc6.cu); 5: one tile per CTA (attn_tc5.cu; SELFTOK_ATTN=tc5)
   std::unordered_map<std::string, Tensor> w;
   std::unordered_map<std::string, WPack> wp;
   std::vector<void*> allocs;            // tables + packed weights
@@ -74,6 +75,7 @@ struct selftok_engine {
   float *enc_mod = nullptr, *enc_pos = nullptr, *cbt = nullptr;
   float *ctx_mod = nullptr, *x_mod = nullptr, *ctx_last_mod = nullptr, *final_mod = nullptr, *dit_pos = nullptr;
   float* rend_x0 = nullptr;
+  int* bad_ids = nullptr;               // device counter of out-of-range token ids seen by the lookup kernel
   DecodeWs dws;
   EncodeWs ews;
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (B, steps) -> (exec, launches)
@@ -219,10 +221,16 @@ extern "C" __attribute__((visibility("default"))) int selftok_create(const selft
   {
     const char* v = getenv("SELFTOK_ATTN");
     if (v && std::string(v) == "mma") e->attn_tcgen05 = false;
+    if (v && std::string(v) == "tc5") e->attn_gen = 5;
   }
   if (tc_mode(e)) {
     int st = gemm_tc_init();
     if (st != 0) { delete e; return st; }
+  }
+  if (cudaMalloc(&e->bad_ids, sizeof(int)) != cudaSuccess || cudaMemset(e->bad_ids, 0, sizeof(int)) != cudaSuccess) {
+    set_error("cudaMalloc failed in selftok_create");
+    delete e;
+    return SELFTOK_ERR_CUDA;
   }
   *out = e;
   return SELFTOK_OK;
@@ -238,6 +246,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_destroy(selftok_ha
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);
   for (auto& kv : e->w) cudaFree(kv.second.d);
   free_pool(e, e->allocs);
+  if (e->bad_ids) cudaFree(e->bad_ids);
   free_dws(e);
   free_ews(e);
   delete e;
@@ -534,7 +543,30 @@ static int run_lookup(selftok_engine* e, const int64_t* tokens, int B, float* ou
   GETW(cb, "encoder.quantizer._codebook.embed");
   GETW(lw, "encoder.final_layer_norm3.weight");
   GETW(lb, "encoder.final_layer_norm3.bias");
-  PROF(PC_OTHER, launch_lookup_ln3(tokens, (int64_t)B * e->cfg.K, cb->d, e->cfg.codebook_size, e->cfg.code_dim, lw->d, lb->d, outs_q, s));
+  PROF(PC_OTHER, launch_lookup_ln3(tokens, (int64_t)B * e->cfg.K, cb->d, e->cfg.codebook_size, e->cfg.code_dim, lw->d, lb->d, outs_q,
+                                   e->bad_ids, s));
+  return 0;
+}
+
+// Synchronises `stream`, returns how many token ids outside [0, codebook_size) the lookups on this handle have seen since
+// the last call (their rows were poisoned with NaN) and resets the counter; < 0 on a CUDA error.
+extern "C" __attribute__((visibility("default"))) int64_t selftok_id_errors(selftok_handle_t e, void* stream) {
+  if (!e || !e->bad_ids) return -1;
+  int n = 0;
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) return -1;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(&n, e->bad_ids, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) return -1;
+  if (cudaMemsetAsync(e->bad_ids, 0, sizeof(int), s) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+  return n;
+}
+static int check_ids_after_sync(selftok_engine* e, void* stream, const char* who) {
+  const int64_t n = selftok_id_errors(e, stream);
+  STK_CHECK(n >= 0, SELFTOK_ERR_CUDA, "selftok_id_errors failed");
+  if (n > 0) {
+    set_error(std::string(who) + ": " + std::to_string(n) + " token id(s) outside [0, codebook_size)");
+    return SELFTOK_ERR_BAD_ARG;
+  }
   return 0;
 }
 
@@ -679,7 +711,8 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       ao.fp16 = fp16;
       const int ctx_rows = ctx_self ? Kc : 0, ctx_keys = ctx_self ? Kc : 0;
       if (nsplit(e) == 1 && e->attn_tcgen05)
-        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16));
+        PROF(PC_ATTN, e->attn_gen == 6 ? launch_attention_tc6(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16)
+                                       : launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16));
       else
         PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, fp16));
       // post_attention (mmdit.py:485-496); the pre_only context block of the last layer stops here
@@ -726,7 +759,8 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
       ao.fp16 = is_fp16(e);
       if (nsplit(e) == 1 && e->attn_tcgen05)
-        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e)));
+        PROF(PC_ATTN, e->attn_gen == 6 ? launch_attention_tc6(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e))
+                                       : launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e)));
       else
         PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, is_fp16(e)));
     }
@@ -764,7 +798,9 @@ static int dit_forward(selftok_engine* e, int B, int step, cudaStream_t s) {
   ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
   STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
   PROF(PC_OTHER, launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
-  return joint_blocks(e, B, Kc, step, /*ctx_self=*/false, s);
+  // context rows see the image keys unless the handle was created with context_see_xt = 0 (sd3/mmdit.py:1012,1060; the
+  // reference pipeline's sampler passes context_see_xt=True, SelftokPipeline.py:259)
+  return joint_blocks(e, B, Kc, step, /*ctx_self=*/e->cfg.context_see_xt == 0, s);
 }
 
 static int decode_body(selftok_engine* e, int B, int steps, cudaStream_t s) {
@@ -894,7 +930,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_decode_host(selfto
   STK_TRY(selftok_decode(e, w.tokens, w.x_lat, B, steps, w.x_lat, stream));
   STK_CUDA(cudaMemcpyAsync(x0_out_host, w.x_lat, sizeof(float) * nlat, cudaMemcpyDeviceToHost, s));
   STK_CUDA(cudaStreamSynchronize(s));
-  return SELFTOK_OK;
+  return check_ids_after_sync(e, stream, "selftok_decode_host");
 }
 
 extern "C" __attribute__((visibility("default"))) int selftok_render_host(selftok_handle_t e, const int64_t* tokens_host, int B, float* x0_out_host, void* stream) {
@@ -909,7 +945,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_render_host(selfto
   STK_TRY(selftok_render(e, w.tokens, B, w.x_lat, stream));
   STK_CUDA(cudaMemcpyAsync(x0_out_host, w.x_lat, sizeof(float) * nlat, cudaMemcpyDeviceToHost, s));
   STK_CUDA(cudaStreamSynchronize(s));
-  return SELFTOK_OK;
+  return check_ids_after_sync(e, stream, "selftok_render_host");
 }
 
 extern "C" __attribute__((visibility("default"))) int selftok_set_profile(selftok_handle_t e, int enable) {
@@ -996,9 +1032,11 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_f32(co
 
 extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(const float* qkv, float* out, int B, int S, int H, int ns, int ctx_rows, int ctx_keys,
                                       void* stream) {
-  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3 || ns == 10 || ns == 11), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
-  const bool tc5 = ns >= 10;                    // 10: tcgen05 kernel, IEEE half; 11: tcgen05 kernel, bf16
-  const int fp16 = ns == 0 || ns == 10;
+  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3 || ns == 10 || ns == 11 || ns == 20 || ns == 21), SELFTOK_ERR_BAD_ARG,
+            "selftok_k_attention_tc: bad argument");
+  const bool tc6 = ns >= 20;                    // 20 / 21: four-stream tcgen05 kernel (attn_tc6.cu), IEEE half / bf16
+  const bool tc5 = ns >= 10 && !tc6;            // 10 / 11: one-tile-per-CTA tcgen05 kernel (attn_tc5.cu), IEEE half / bf16
+  const int fp16 = ns == 0 || ns == 10 || ns == 20;
   if (ns != 3) ns = 1;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n = (int64_t)B * S * 3 * H * 64;
@@ -1008,7 +1046,8 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(con
   int st = launch_split_bf16(qkv, qh, ql, n, s, fp16);
   AttnOut ao;
   ao.f32_a = out; ao.split = S; ao.ld = (int64_t)H * 64;
-  if (!st && tc5) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
+  if (!st && tc6) st = launch_attention_tc6(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
+  else if (!st && tc5) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
   else if (!st) st = launch_attention_tc(qh, ql, B, S, H, ns, ctx_rows, ctx_keys, ao, s, fp16);
   cudaStreamSynchronize(s);
   cudaFree(qh);

@@ -73,8 +73,9 @@ int launch_attention_f32(const float* q, int64_t q_ld, int64_t q_bs, const float
 int launch_vq(const float* z, int64_t R, int Q, const float* w_in, const float* b_in, const float* codebook,
               const float* codebook_t, int n_codes, int code_dim, const float* ln_w, const float* ln_b,
               int64_t* ids, float* outs_q, cudaStream_t s);
+// ids outside [0, n_codes): row poisoned with NaN and counted in *bad_ids (may be NULL)
 int launch_lookup_ln3(const int64_t* ids, int64_t R, const float* codebook, int n_codes, int code_dim,
-                      const float* ln_w, const float* ln_b, float* outs_q, cudaStream_t s);
+                      const float* ln_w, const float* ln_b, float* outs_q, int* bad_ids, cudaStream_t s);
 // [B,C,Hh,Ww] latents -> [B*(Hh/p)*(Ww/p), C*p*p] patch rows ((c,ph,pw) fastest-last, Conv2d weight order)
 int launch_patchify(const float* x, float* out, int B, int C, int Hh, int Ww, int p, cudaStream_t s);
 // x_lat[b,c,h*p+ph,w*p+pw] = x_in[...] - dt * o[b, h*g+w, (ph*p+pw)*C + c]   (unpatchify + Euler; dt = -1 & x_in NULL: plain unpatchify)
@@ -111,6 +112,10 @@ int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo
 
 // tcgen05 / TMEM attention (attn_tc5.cu), single-pass 16-bit operands (fp16 != 0: IEEE half, else bf16)
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
+                         cudaStream_t s, int fp16);
+
+// four-stream tcgen05 / TMEM attention (attn_tc6.cu): two query tiles per CTA sharing K / V, one thread per query row
+int launch_attention_tc6(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16);
 
 }  // namespace stk

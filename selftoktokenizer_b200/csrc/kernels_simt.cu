@@ -755,13 +755,20 @@ int launch_vq(const float* z, int64_t R, int Q, const float* w_in, const float* 
   return 0;
 }
 
+// An id outside [0, n_codes) is an ERROR, as `codebook[idx]` is in the reference (vector_quantize_pytorch.py:310-314 raises /
+// device-asserts): the row is poisoned with NaN and counted in *bad_ids, which the engine reports (selftok_id_errors; the
+// host-buffer entry points return SELFTOK_ERR_BAD_ARG).  Nothing is clamped silently.
 __global__ void lookup_ln3_kernel(const int64_t* __restrict__ ids, int64_t R, const float* __restrict__ codebook,
                                   int n_codes, int dim, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
-                                  float* __restrict__ outs_q) {
+                                  float* __restrict__ outs_q, int* __restrict__ bad_ids) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= R) return;
-  int64_t id = ids[row];
-  id = id < 0 ? 0 : (id >= n_codes ? n_codes - 1 : id);
+  const int64_t id = ids[row];
+  if (id < 0 || id >= n_codes) {
+    if (bad_ids) atomicAdd(bad_ids, 1);
+    for (int d = 0; d < dim; ++d) outs_q[row * dim + d] = __int_as_float(0x7fc00000);
+    return;
+  }
   float mean = 0.f;
   for (int d = 0; d < dim; ++d) mean += codebook[id * dim + d];
   mean /= (float)dim;
@@ -772,9 +779,9 @@ __global__ void lookup_ln3_kernel(const int64_t* __restrict__ ids, int64_t R, co
 }
 
 int launch_lookup_ln3(const int64_t* ids, int64_t R, const float* codebook, int n_codes, int code_dim,
-                      const float* ln_w, const float* ln_b, float* outs_q, cudaStream_t s) {
+                      const float* ln_w, const float* ln_b, float* outs_q, int* bad_ids, cudaStream_t s) {
   STK_CHECK(ids && codebook && ln_w && ln_b && outs_q && R > 0, -1, "lookup: bad arguments");
-  lookup_ln3_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(ids, R, codebook, n_codes, code_dim, ln_w, ln_b, outs_q);
+  lookup_ln3_kernel<<<(unsigned)((R + 127) / 128), 128, 0, s>>>(ids, R, codebook, n_codes, code_dim, ln_w, ln_b, outs_q, bad_ids);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

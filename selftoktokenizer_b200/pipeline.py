@@ -98,7 +98,16 @@ class SelftokPipeline:
             raise SelftokError("cfg_scale != 1 is not on the shipped path (the reference never forwards it: "
                                "rectified_flow.py:173 default uncond_scale=1.0)")
         self.device = torch.device(device if device is not None else "cuda")
-        self.dims = dims if dims is not None else SelftokDims.from_cfg(cfg)
+        # `datasize` (a CLI argument of the reference's test.py) sets the latent side: the models are built from the cfg but
+        # run at datasize // 8 through the centre-cropped positional grids (models_ours.py:183-202, sd3/mmdit.py:877-896)
+        self.dims = dims if dims is not None else SelftokDims.from_cfg(cfg, datasize)
+        if not self.dims.renderer:
+            # the sampler call hard-codes context_see_xt=True whatever the YAML says (SelftokPipeline.py:259); the renderer
+            # call passes nothing, i.e. False (SelftokPipeline.py:310, sd3/mmdit.py:1533) -- the engine does that by itself
+            import dataclasses
+            self.dims = dataclasses.replace(self.dims, context_see_xt=True)
+        if self.dims.latent * 8 != int(datasize):
+            raise SelftokError(f"datasize {datasize} does not match the engine geometry (latent side {self.dims.latent})")
         self.vae = vae
         if self.vae is None and sd3_path:
             self.vae = _load_vae(sd3_path, self.device, self.dtype)
@@ -138,12 +147,22 @@ class SelftokPipeline:
         latent_dim = self.datasize // 8
         if noise is None:
             noise = torch.randn(B, self.dims.in_channels, latent_dim, latent_dim)
-        return self.engine.decode(token_idx, noise)
+        out = self.engine.decode(token_idx, noise)
+        self._raise_on_bad_ids(token_idx)
+        return out
+
+    def _raise_on_bad_ids(self, token_idx) -> None:
+        # `codebook[idx]` raises for ids outside the codebook in the reference (vector_quantize_pytorch.py:310-314); host ids were
+        # checked before the launch, device ids are counted by the lookup kernel
+        if token_idx.is_cuda and self.engine.id_errors() > 0:
+            raise IndexError("token id out of range for the codebook")
 
     @torch.no_grad()
     def render_latents(self, idx) -> torch.Tensor:
         token_idx = torch.from_numpy(idx) if isinstance(idx, np.ndarray) else idx
-        return self.engine.render(token_idx)
+        out = self.engine.render(token_idx)
+        self._raise_on_bad_ids(token_idx)
+        return out
 
     # ------------------------------------------------------------------ reference API (pixel space, needs the SD3 VAE)
     def _need_vae(self):

@@ -141,10 +141,36 @@ def synth_tensor(name: str, shape, kind: str, std: float, seed: int = 0, device=
     return t.view(shape).contiguous()
 
 
-def synth_state_dict(d: SelftokDims, seed: int = 0, device="cpu", include_aux: bool = True) -> Dict[str, torch.Tensor]:
+def _stress(name: str, t: torch.Tensor, kind: str, seed: int) -> torch.Tensor:
+    """Numerically hostile variant of a decoder GEMM weight (fp16-operand stress fixture): heavy-tailed entries (a u + b u^9
+    mix of the uniform hash value with the same std: max/std 1.7 -> 4.0) and, in every `attn.qkv` / `mlp.fc1` matrix,
+    four output channels scaled by x30 .. x100 -- the outlier channels real SD3-derived checkpoints are known for.
+    Pure elementwise fp32 arithmetic on the hashed values: bit-identical on any host and device."""
+    if kind != "w" or not name.startswith("model.joint_blocks."):
+        return t
+    flat = t.reshape(t.shape[0], -1)
+    amax = flat.abs().max().clamp_min(1e-30)              # an exact hashed value: no reduction-order dependence
+    u = flat / amax                                       # uniform on [-1, 1]
+    u3 = u * u * u
+    heavy = 0.2 * u + 2.0128 * (u3 * u3 * u3)             # 0.2 u + 0.8 sqrt(19/3) u^9: same std (0.95x), max/std 1.7 -> 4.0
+    out = heavy * amax
+    if name.endswith("attn.qkv.weight") or name.endswith("mlp.fc1.weight"):
+        key = zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1 & 0xFFFFFFFF)
+        rows = out.shape[0]
+        for i in range(4):
+            r = (key * (2 * i + 3) + 977 * i) % rows
+            gain = 30.0 + float((key >> (4 * i)) % 71)
+            out[r] = out[r] * gain
+    return out.reshape(t.shape).contiguous()
+
+
+def synth_state_dict(d: SelftokDims, seed: int = 0, device="cpu", include_aux: bool = True,
+                     stress: bool = False) -> Dict[str, torch.Tensor]:
     sd: Dict[str, torch.Tensor] = OrderedDict()
     for name, (shape, kind, std) in state_dict_spec(d).items():
         sd[name] = synth_tensor(name, shape, kind, std, seed, device)
+        if stress:
+            sd[name] = _stress(name, sd[name], kind, seed)
     if include_aux:
         # buffers the reference's eval forward consults (vector_quantize_pytorch.py:421-444,555,864-866):
         # `initted`=1 (else eval runs k-means), `continuous`=0.

@@ -57,6 +57,9 @@ def test_config_surface():
     d = C.SelftokDims.from_cfg(cfg)
     assert repr(cfg) == before, "from_cfg must not mutate cfg (the reference does; consciously dropped)"
     assert d == C.FULL and d.dit_hidden == 1536 and d.n_img == 256 and d.enc_n_img == 256
+    for yml, K, rend in (("selftok_256_1024tok.yml", 1024, False), ("selftok_renderer_1024tok.yml", 1024, True)):
+        dk = C.SelftokDims.from_cfg(C.parse_args_from_yaml(os.path.join(REPO, "configs", yml)))
+        assert dk.K == K and dk.renderer is rend and sum(dk.k_per_stage) == K and dk.latent == 32
     r = C.SelftokDims.from_cfg(C.parse_args_from_yaml(os.path.join(REPO, "configs/selftok_renderer_512tok.yml")))
     assert r.renderer and not r.context_see_xt and r.stages == (1000,)
     with pytest.raises(KeyError):

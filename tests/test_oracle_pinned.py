@@ -1,6 +1,7 @@
 """Pins oracle/selftok_oracle.py (the CPU restatement) against the fixtures that oracle/gen_golden.py produced by
 running the UNMODIFIED reference modules, and — when /root/reference is mounted — against the live modules."""
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -191,3 +192,100 @@ def test_c_diti_schedule_matches_reference_fixture(gold, name, dims):
     k = co.diti_k(g["timestep_map"].astype(np.int64), dims.stages, dims.k_per_stage, dims.K)
     assert (k == g["k"]).all()
     assert (k == S.make_tables(dims.K, dims.stages, dims.k_per_stage).k.numpy()).all()
+
+
+# ------------------------------------------------------------------ SD3 VAE restatement (oracle/vae_oracle.py)
+def test_vae_oracle_matches_reference_fixture(gold):
+    """decoder + encoder of the reference's in-tree SDVAE (ch = 32, seeded synthetic weights) as recorded by
+    oracle/gen_golden.py vae_tiny."""
+    import vae_oracle as V
+    g = gold("vae_tiny")
+    sd = synth.synth_vae_state_dict(ch=32)
+    z = synth.synth_tensor("golden.vae.z", (2, 16, 8, 8), "emb", 1.0)
+    x = synth.synth_tensor("golden.vae.x", (2, 3, 64, 64), "emb", 0.5)
+    assert np.abs(V.decode(sd, z).numpy() - g["dec"]).max() < 2e-5
+    assert np.abs(V.encode_moments(sd, x).numpy() - g["moments"]).max() < 2e-5
+
+
+def test_pixel_fixture_is_reference_latents_through_the_vae_oracle(gold):
+    """tests/golden/tiny_pixels.npz == images_from_latents(reference pred_x0): the pixel end of SelftokPipeline.decoding
+    (process_out -> vae.decode -> norm_ip, SelftokPipeline.py:284-294) restated in vae_oracle."""
+    import vae_oracle as V
+    g, gp = gold("tiny"), gold("tiny_pixels")
+    px = V.images_from_latents(synth.synth_vae_state_dict(ch=32, encoder=False), torch.from_numpy(g["pred_x0"]))
+    assert px.min() >= 0 and px.max() <= 1
+    assert np.abs(px.numpy() - gp["pixels"]).max() < 2e-5
+
+
+def test_boundary_helpers_match_the_live_reference():
+    """a13: NormalizeToTensor, norm_ip, SD3LatentFormat against the reference's own definitions
+    (SelftokPipeline.py:85-97,135-137; sd3/sd3_impls.py:133-144)."""
+    from selftoktokenizer_b200 import pipeline as P
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, size=(24, 40, 3)).astype(np.uint8)
+    t = P.NormalizeToTensor()(img)
+    assert t.shape == (3, 24, 40) and t.dtype == torch.float32
+    assert float(t.min()) >= -1.0 and float(t.max()) <= 1.0
+    assert torch.equal(t, torch.from_numpy((img.astype(np.float32) / 127.5 - 1.0).astype(np.float32).transpose(2, 0, 1)))
+    grey = P.NormalizeToTensor()(img[:, :, 0])                       # 2-D input gains a channel axis (reshape=True)
+    assert grey.shape == (1, 24, 40)
+    x = torch.tensor([-3.0, -1.0, 0.0, 0.5, 1.0, 2.0])
+    y = x.clone()
+    P.norm_ip(y, -1, 1)
+    assert torch.equal(y, torch.tensor([0.0, 0.0, 0.5, 0.75, 1.0, 1.0]))
+    lat = torch.randn(2, 16, 4, 4)
+    f = P.SD3LatentFormat()
+    assert torch.allclose(f.process_out(f.process_in(lat)), lat, atol=1e-6)
+    assert torch.equal(f.process_in(lat), (lat - 0.0609) * 1.5305)
+    import ref_loader
+    if not ref_loader.reference_available():
+        return
+    ref_loader.import_reference()
+    from mimogpt.infer import SelftokPipeline as SP
+    from mimogpt.models.selftok.sd3.sd3_impls import SD3LatentFormat as RefFmt
+    assert torch.equal(SP.NormalizeToTensor()(img), t)
+    y2 = x.clone()
+    SP.norm_ip(y2, -1, 1)
+    assert torch.equal(y2, y)
+    assert torch.equal(RefFmt().process_in(lat), f.process_in(lat)) and torch.equal(RefFmt().process_out(lat), f.process_out(lat))
+
+
+def test_ema_decoder_state_selection():
+    """ema_decoder=True swaps the MMDiT weights for checkpoint['ema_state_dict'] (keys without the 'model.' prefix),
+    encoder keys untouched (SelftokPipeline.py:190-199)."""
+    from selftoktokenizer_b200.pipeline import _decoder_state
+    ck = {"encoder.a": torch.ones(2), "model.w": torch.zeros(3), "model.b": torch.zeros(1), "epoch": 3,
+          "ema_state_dict": {"w": torch.full((3,), 7.0), "b": torch.full((1,), 9.0)}}
+    plain = _decoder_state(ck, False)
+    assert set(plain) == {"encoder.a", "model.w", "model.b"} and float(plain["model.w"][0]) == 0.0
+    ema = _decoder_state(ck, True)
+    assert set(ema) == {"encoder.a", "model.w", "model.b"}
+    assert float(ema["model.w"][0]) == 7.0 and float(ema["model.b"][0]) == 9.0 and float(ema["encoder.a"][0]) == 1.0
+
+
+def test_config_validation_raises_not_asserts():
+    import dataclasses
+    with pytest.raises(ValueError):
+        dataclasses.replace(C.TINY, k_per_stage=(1, 1, 1, 1, 1)).validate()
+    with pytest.raises(ValueError):
+        dataclasses.replace(C.TINY, latent=7).validate()
+    cfg = C.parse_args_from_yaml(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs/selftok_256_512tok.yml"))
+    cfg.tokenizer.params.quantizer_config["continuous"] = True
+    with pytest.raises(ValueError):
+        C.SelftokDims.from_cfg(cfg)
+    # datasize overrides the latent side (the reference's CLI argument), the positional grids stay the checkpoint's
+    cfg = C.parse_args_from_yaml(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs/selftok_256_512tok.yml"))
+    d = C.SelftokDims.from_cfg(cfg, datasize=512)
+    assert d.latent == 64 and d.enc_pos_max == 64 and d.dit_pos_max == 192 and d.n_img == 1024
+
+
+def test_mid_fixture_oracle(gold):
+    """B = 4 on the mid-size geometry: the restatement reproduces the reference's tokens and 50-step result."""
+    g = gold("mid")
+    d = C.MID
+    sd = synth.synth_state_dict(d)
+    x0 = synth.synth_tensor("golden.mid.x0", (4, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    _, tok, _ = O.encode(sd, d, x0)
+    assert np.array_equal(tok.numpy(), g["tokens"])
+    x = O.decode(sd, d, tok, torch.from_numpy(g["noise"]), truncate=True)
+    assert np.abs(x.numpy() - g["pred_x0"]).max() < 2e-5

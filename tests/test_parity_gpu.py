@@ -33,11 +33,12 @@ def tiny_engine(request, tiny_sd):
 
 
 def _check_tokens(tok, gold_tok, margin, what):
+    """Token ids must be BIT-EXACT on the committed fixtures (north_star).  Every mismatch is printed with the reference's own
+    top-1/top-2 cosine margin so that a rounding-level tie can be told from a real error -- but none is tolerated."""
     mism = tok != gold_tok
     if mism.any():
-        print(f"[{what}] {int(mism.sum())} / {mism.size} token mismatches; reference margins: {margin[mism]}")
-    assert (margin[mism] < 1e-4).all(), f"{what}: token mismatch at a non-tie"
-    assert mism.mean() <= 0.005
+        print(f"[{what}] {int(mism.sum())} / {mism.size} token mismatches; reference margins: {margin[mism] if margin is not None else '?'}")
+    assert int(mism.sum()) == 0, f"{what}: {int(mism.sum())} token ids differ from the reference"
 
 
 def test_tiny_encode_tokens_bit_exact(tiny_engine, gold):
@@ -246,3 +247,257 @@ def test_full_batch_roundtrip_properties(full_engine):
     tok_h = torch.empty(64, d.K, dtype=torch.int64).pin_memory()
     full_engine.encode_host(x0.cpu().pin_memory(), tok_h)
     assert torch.equal(tok_h, tok.cpu())
+
+
+# ------------------------------------------------------------------------------------------------ round-2 hardening
+def _top2_margin(sd, z):
+    zn = torch.nn.functional.normalize(torch.nn.functional.linear(z, sd["encoder.quantizer.project_in.weight"],
+                                                                  sd["encoder.quantizer.project_in.bias"]), dim=-1)
+    cb = sd["encoder.quantizer._codebook.embed"][0]
+    out = []
+    flat = zn.reshape(-1, zn.shape[-1])
+    for lo in range(0, flat.shape[0], 4096):
+        t2 = (flat[lo:lo + 4096] @ cb.t()).topk(2, dim=-1).values
+        out.append(t2[:, 0] - t2[:, 1])
+    return torch.cat(out).reshape(z.shape[:-1]).numpy()
+
+
+def test_full_batch64_tokens_bit_exact_against_oracle(full_engine):
+    """BASELINE batch: all 64 x 512 = 32768 token ids of the bench latents against the (pinned) oracle run on the host
+    cores in this test -- zero mismatches allowed; the reference's margins go down to 1e-5 at this sample size."""
+    d = C.FULL
+    x0 = synth.synth_tensor("bench.x0.0", (64, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    spec = synth.state_dict_spec(d)
+    sd = {n: synth.synth_tensor(n, sh, k, std) for n, (sh, k, std) in spec.items() if n.startswith("encoder.")}
+    tb = S.make_tables(d.K, d.stages, d.k_per_stage)
+    toks, zs = [], []
+    with torch.no_grad():
+        for lo in range(0, 64, 8):
+            _, t, z = O.encode(sd, d, x0[lo:lo + 8], tb)
+            toks.append(t)
+            zs.append(z)
+    tok_ref, z_ref = torch.cat(toks), torch.cat(zs)
+    margin = _top2_margin(sd, z_ref)
+    print(f"oracle B=64 encode done; smallest reference top-1/top-2 margin {margin.min():.3e}, {int((margin < 1e-4).sum())} below 1e-4")
+    tok = full_engine.encode(x0).cpu()
+    _check_tokens(tok.numpy(), tok_ref.numpy(), margin, "full B=64 encode")
+    assert (tok_ref[0] != tok_ref[1]).float().mean() > 0.3
+
+
+class _OracleVAE:
+    """Stand-in for diffusers.AutoencoderKL with the reference's call shapes (SelftokPipeline.py:215,288,316): the SD3 VAE
+    arithmetic comes from oracle/vae_oracle.py (the checker; fp32 on the host) -- it is the VAE here, not the path."""
+
+    class _Dist:
+        def __init__(self, m):
+            self._m = m
+
+        def mode(self):
+            return self._m
+
+    def __init__(self, sd, ch_mult=(1, 2, 4, 4)):
+        self.sd, self.ch_mult = sd, ch_mult
+
+    def encode(self, x, return_dict=False):
+        import vae_oracle as V
+        return (self._Dist(V.encode_mean(self.sd, x.float().cpu()).to(x.device)),)
+
+    def decode(self, z, return_dict=False):
+        import vae_oracle as V
+        return (V.decode(self.sd, z.float().cpu()).to(z.device),)
+
+
+def _psnr(a, b):
+    return 10.0 * np.log10(1.0 / max(float(((a - b) ** 2).mean()), 1e-30))
+
+
+def _pixel_gate(px, px_ref, gt, what):
+    """north_star bar at the PIXEL boundary: max-abs <= 1e-3 on [0,1] images and PSNR (against the same target image) within
+    0.01 dB of the reference's reconstruction."""
+    err = float(np.abs(px - px_ref).max())
+    d_psnr = abs(_psnr(px, gt) - _psnr(px_ref, gt))
+    print(f"[{what}] pixels: max-abs err {err:.3e}; PSNR vs target ours {_psnr(px, gt):.4f} dB / reference {_psnr(px_ref, gt):.4f} dB "
+          f"(delta {d_psnr:.5f} dB); PSNR ours-vs-reference {_psnr(px, px_ref):.1f} dB")
+    assert err <= 1e-3, what
+    assert d_psnr <= 0.01, what
+
+
+def test_tiny_pixel_gate_through_pipeline_api(tiny_sd, gold):
+    """encoding() / decoding() of the drop-in class with a VAE object of the reference's shape (the in-tree SDVAE arithmetic,
+    ch = 32): pixels of the 50-step decode against the reference's own pixels (tests/golden/tiny_pixels.npz)."""
+    import vae_oracle as V
+    from selftoktokenizer_b200 import SelftokPipeline
+    g, gp = gold("tiny"), gold("tiny_pixels")
+    d = C.TINY
+    vsd = synth.synth_vae_state_dict(ch=32)
+    for precision in ("fp16", "bf16x3"):
+        pipe = SelftokPipeline(cfg=None, ckpt_path=None, sd3_path=None, datasize=d.latent * 8, dtype=torch.float32, device=DEV,
+                               state_dict=tiny_sd, dims=d, vae=_OracleVAE(vsd), precision=precision)
+        torch.manual_seed(1234)                                       # the reference's noise draw (CPU global generator)
+        rec = pipe.decoding(g["tokens"], DEV)
+        assert rec.dtype == torch.float32 and tuple(rec.shape) == (3, 3, 64, 64)
+        x0 = synth.synth_tensor("golden.tiny.x0", (3, d.in_channels, d.latent, d.latent), "emb", 1.0)
+        gt = V.images_from_latents(vsd, x0).numpy()
+        _pixel_gate(rec.cpu().numpy(), gp["pixels"], gt, f"tiny decoding() {precision}")
+        # encoding(): images -> VAE -> process_in -> tokens; against the oracle run on the same VAE latents
+        img = synth.synth_tensor("tiny.images", (2, 3, 64, 64), "emb", 0.5)
+        tok = pipe.encoding(img, DEV)
+        lat = V.latents_from_images(vsd, img)
+        _, tok_ref, z_ref = O.encode(tiny_sd, d, lat)
+        _check_tokens(tok.cpu().numpy(), tok_ref.numpy(), _top2_margin(tiny_sd, z_ref), f"tiny encoding() {precision}")
+        pipe.engine.close()
+
+
+def test_full_pixel_gate(full_engine, gold):
+    """The pixel-boundary parity gate at the full geometry (B = 1): our 50-step latents through the SD3 VAE arithmetic
+    (oracle, ch = 128, seeded weights) against the reference's latents through the reference's own SDVAE
+    (tests/golden/full_pixels.npz)."""
+    import vae_oracle as V
+    g, ge, gp = gold("full_decode"), gold("full_encode"), gold("full_pixels")
+    d = C.FULL
+    vsd = synth.synth_vae_state_dict(ch=128, encoder=False)
+    tok = torch.from_numpy(ge["tokens"][:1])
+    x = full_engine.decode(tok, torch.from_numpy(g["noise"])).cpu()
+    with torch.no_grad():
+        px = V.images_from_latents(vsd, x).numpy()
+        x0 = synth.synth_tensor("golden.full.x0", (2, d.in_channels, d.latent, d.latent), "emb", 1.0)[:1]
+        gt = V.images_from_latents(vsd, x0).numpy()
+    _pixel_gate(px, gp["pixels"], gt, f"full decode {full_engine.precision}")
+
+
+def test_full_renderer_pixel_gate(gold):
+    import vae_oracle as V
+    from selftoktokenizer_b200.capi import Engine
+    gr, ge, gp = gold("full_renderer"), gold("full_encode"), gold("full_pixels")
+    d = dataclasses.replace(C.FULL, renderer=True)
+    vsd = synth.synth_vae_state_dict(ch=128, encoder=False)
+    eng = Engine(d, synth.synth_state_dict(d, device=DEV), device=DEV, precision="auto")
+    assert eng.precision == "bf16x3"
+    r = eng.render(torch.from_numpy(ge["tokens"][:1])).cpu()
+    eng.close()
+    with torch.no_grad():
+        px = V.images_from_latents(vsd, r).numpy()
+        x0 = synth.synth_tensor("golden.full.x0", (2, d.in_channels, d.latent, d.latent), "emb", 1.0)[:1]
+        gt = V.images_from_latents(vsd, x0).numpy()
+    _pixel_gate(px, gp["renderer_pixels"], gt, "full renderer bf16x3")
+
+
+@pytest.mark.parametrize("fixture,stress", [("mid", False), ("mid_stress", True)])
+def test_mid_batch4_decode_and_fp16_stress(fixture, stress, gold):
+    """B = 4 on the mid-size geometry (multi-tile attention / GEMMs), against the reference's own run.  `mid_stress` is the
+    same run on the heavy-tailed checkpoint with x30..x100 outlier channels in every qkv / fc1 matrix: the fp16-operand
+    stress test.  bf16x3 must stay fp32-faithful; fp16 is measured, and must hold the 1e-3 bar here (if a checkpoint breaks
+    it, `precision='auto'` detects that and falls back: test_auto_precision_probe)."""
+    from selftoktokenizer_b200.capi import Engine
+    g = gold(fixture)
+    d = C.MID
+    sd = synth.synth_state_dict(d, stress=stress)
+    x0 = synth.synth_tensor("golden.mid.x0", (4, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    tok_ref, noise = torch.from_numpy(g["tokens"]), torch.from_numpy(g["noise"])
+    for precision, tol_v, tol_x in (("bf16x3", 2e-4, 1e-4), ("fp16", 4e-3, 1e-3)):
+        eng = Engine(d, sd, device=DEV, precision=precision)
+        tok = eng.encode(x0).cpu()
+        _check_tokens(tok.numpy(), g["tokens"], g["margin"], f"{fixture} encode")
+        ev = max(float(np.abs(eng.dit_velocity(tok_ref, noise, st).cpu().numpy() - g[f"v{st}"]).max()) for st in (0, 49))
+        x = eng.decode(tok_ref, noise).cpu().numpy()
+        ex = float(np.abs(x - g["pred_x0"]).max())
+        print(f"[{fixture} {precision}] B=4: velocity max-abs err {ev:.3e}, 50-step latents {ex:.3e} (finite: {np.isfinite(x).all()})")
+        assert np.isfinite(x).all()
+        assert ev < tol_v and ex < tol_x
+        eng.close()
+
+
+def test_auto_precision_probe(gold):
+    """precision='auto' keeps single-pass fp16 only if a probe on THIS checkpoint agrees with bf16x3; a checkpoint whose
+    outlier channels push half-precision operands past the bar gets the fp32-faithful mode."""
+    from selftoktokenizer_b200.capi import Engine
+    d = C.MID
+    eng = Engine(d, synth.synth_state_dict(d), device=DEV, precision="auto")
+    print("auto probe (benign checkpoint):", eng.auto_probe)
+    assert eng.precision == "fp16" and eng.auto_probe["chosen"] == "fp16" and eng.auto_probe["dev"] <= eng.auto_probe["tol"]
+    eng.close()
+    sd = synth.synth_state_dict(d, stress=True)
+    for name in list(sd):                                  # brutal variant: the outlier rows another x40
+        if name.startswith("model.joint_blocks.") and (name.endswith("mlp.fc1.weight") or name.endswith("attn.qkv.weight")):
+            w = sd[name]
+            rn = w.norm(dim=1)
+            w[rn > 10 * rn.median()] *= 40.0
+    eng = Engine(d, sd, device=DEV, precision="auto")
+    print("auto probe (brutal outliers):", eng.auto_probe)
+    assert eng.auto_probe["chosen"] == eng.precision
+    assert eng.precision == "bf16x3" and eng.auto_probe["dev"] > eng.auto_probe["tol"]
+    g = gold("mid")
+    x = eng.decode(torch.from_numpy(g["tokens"]), torch.from_numpy(g["noise"]))
+    assert torch.isfinite(x).all()
+    eng.close()
+
+
+def test_shape_and_id_checks(tiny_engine):
+    """Wrong-resolution latents, short token rows and out-of-range ids fail loudly (the reference's
+    `codebook[idx]` raises)."""
+    from selftoktokenizer_b200.capi import SelftokError
+    d = C.TINY
+    tok = torch.zeros(2, d.K, dtype=torch.int64)
+    noise = torch.zeros(2, d.in_channels, d.latent, d.latent)
+    with pytest.raises(SelftokError):
+        tiny_engine.encode(torch.zeros(2, d.in_channels, d.latent * 2, d.latent * 2))
+    with pytest.raises(SelftokError):
+        tiny_engine.decode(tok, torch.zeros(2, d.in_channels, d.latent + 2, d.latent + 2))
+    with pytest.raises(SelftokError):
+        tiny_engine.decode(tok[:, : d.K - 1], noise)
+    with pytest.raises(SelftokError):
+        tiny_engine.decode(tok[:1], noise)
+    bad = tok.clone()
+    bad[1, 3] = d.codebook_size
+    with pytest.raises(SelftokError):
+        tiny_engine.lookup(bad)                                        # host ids: checked before the launch
+    out = tiny_engine.lookup(bad.to(DEV))                              # device ids: NaN row + counter
+    assert torch.isnan(out[1, 3]).all() and torch.isfinite(out[0]).all()
+    assert tiny_engine.id_errors() == 1 and tiny_engine.id_errors() == 0
+    if tiny_engine.precision == "fp16":
+        res = torch.empty_like(noise).pin_memory()
+        with pytest.raises(SelftokError):
+            tiny_engine.decode_host(bad.pin_memory(), noise.pin_memory(), res)
+        # the C entry itself (no Python-side check): status SELFTOK_ERR_BAD_ARG after the copy-back
+        st = tiny_engine.lib.selftok_decode_host(tiny_engine.h, bad.data_ptr(), noise.data_ptr(), 2, 2, res.data_ptr(), None)
+        assert st == -1 and b"token id" in tiny_engine.lib.selftok_last_error()
+
+
+def test_other_datasize_uses_cropped_positional_grids(tiny_sd, gold):
+    """f4: `datasize` != the checkpoint's image_size (a CLI argument of the reference's test.py).  The TINY checkpoint
+    (image_size 64) at datasize 96: latent 12, both positional grids centre-cropped to 6 x 6; against the reference's own run."""
+    from selftoktokenizer_b200 import SelftokPipeline
+    g = gold("tiny_ds96")
+    d = dataclasses.replace(C.TINY, latent=12)
+    for precision in ("bf16x3", "fp16"):
+        pipe = SelftokPipeline(cfg=None, ckpt_path=None, sd3_path=None, datasize=96, device=DEV, state_dict=tiny_sd, dims=d,
+                               precision=precision)
+        x0 = synth.synth_tensor("golden.tinyds.x0", (2, d.in_channels, 12, 12), "emb", 1.0)
+        _check_tokens(pipe.encode_latents(x0).cpu().numpy(), g["tokens"], g["margin"], "datasize 96 encode")
+        x = pipe.decode_latents(g["tokens"], noise=torch.from_numpy(g["noise"])).cpu().numpy()
+        err = float(np.abs(x - g["pred_x0"]).max())
+        print(f"[{precision}] datasize 96 (latent 12) 50-step decode: max-abs err {err:.3e}")
+        assert err < TOL[precision]
+        pipe.engine.close()
+
+
+def test_full_renderer_1024_tokens(gold):
+    """BASELINE config 4 / f4: ONE renderer pass with 1024 tokens at the full geometry (configs/selftok_renderer_1024tok.yml),
+    B = 1, against the reference's own MMDiT_Renderer on the same seeded checkpoint."""
+    import os
+    from selftoktokenizer_b200.capi import Engine
+    g = gold("full_renderer_1024")
+    cfg = C.parse_args_from_yaml(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs/selftok_renderer_1024tok.yml"))
+    d = C.SelftokDims.from_cfg(cfg)
+    assert d.K == 1024 and d.renderer and d.k_per_stage == (1024,)
+    eng = Engine(d, synth.synth_state_dict(d, device=DEV), device=DEV, precision="auto")
+    r = eng.render(torch.from_numpy(g["tokens"])).cpu().numpy()
+    err = float(np.abs(r - g["pred_x0"]).max())
+    print(f"[{eng.precision}] renderer, 1024 tokens, full geometry: max-abs err {err:.3e} (|x|max {np.abs(g['pred_x0']).max():.2f})")
+    assert err < 1e-3
+    # the 1024-query encoder on the same engine: deterministic, ids in range, image dependent
+    x0 = synth.synth_tensor("golden.full.x0", (2, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    tok = eng.encode(x0)
+    assert tuple(tok.shape) == (2, 1024) and int(tok.min()) >= 0 and int(tok.max()) < d.codebook_size
+    assert torch.equal(tok, eng.encode(x0)) and (tok[0] != tok[1]).float().mean() > 0.3
+    eng.close()
