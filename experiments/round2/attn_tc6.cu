@@ -80,6 +80,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// MMA-issuer flavour: plain polling (no suspend hint) -- experiment switch SELFTOK_ATTN6_MMA_SPIN
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+#ifdef SELFTOK_ATTN6_MMA_SPIN
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (!ok && clock64() - t0 > 8000000000LL) __trap();
+  }
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -208,7 +225,7 @@ struct Attn6Params {
 };
 
 template <bool FP16>
-__global__ void __maxnreg__(88)       // 2 CTAs x 11 warps x 88 registers = 61952 of 65536
+__global__ void __maxnreg__(80)       // 2 CTAs x 11 (allocated as 12) warps x 80 registers: 88 leaves room for one CTA only (measured)
 attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn6Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -309,7 +326,7 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const uint32_t qs = q_s + (2 * s + qb) * Q_BYTES;
           auto issue_qk = [&](int gg, bool last) {                            // S = Q K_gg^T; `last` also releases the Q buffer
             const int st = gg % KV_STAGES;
-            mbar_wait(kv_full(st), (gg / KV_STAGES) & 1);
+            mbar_wait_spin(kv_full(st), (gg / KV_STAGES) & 1);
             tc_fence_after();
             const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
 #pragma unroll
@@ -328,7 +345,7 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             const int st = g % KV_STAGES;
             if (j < n_mine) {
               const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
-              mbar_wait(p_ready(s), t & 1);                                    // P_t in TMEM, O rescaled (or read out)
+              mbar_wait_spin(p_ready(s), t & 1);                               // P_t in TMEM, O rescaled (or read out)
               TRACE(10, g);
               tc_fence_after();
 #pragma unroll
@@ -373,26 +390,24 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tc_fence_after();
           const int k0 = j * BKV;
           const bool masked_tile = k0 + BKV > kmax_w;                    // warp-uniform: some row of the warp loses keys here
-          // ---- pass 1: row maximum over the 64 scores (both halves in flight at once; nothing else is live)
-          float mx;
-          {
-            uint32_t a[32], c[32];
-            tmem_ld32(s_tmem, a);
-            tmem_ld32(s_tmem + 32, c);
+          // ---- pass 1: row maximum over the 64 scores, one 32-column half at a time (80 registers per thread)
+          float mx = -INFINITY;
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t a[32];
+            tmem_ld32(s_tmem + 32 * hh, a);
             tmem_ld_wait();
             if (masked_tile) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (k0 + i >= kmax) a[i] = 0xff800000u;                  // -inf
-                if (k0 + 32 + i >= kmax) c[i] = 0xff800000u;
-              }
+              for (int i = 0; i < 32; ++i)
+                if (k0 + 32 * hh + i >= kmax) a[i] = 0xff800000u;        // -inf
             }
             float mp[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) mp[i] = fmaxf(__uint_as_float(a[i]), __uint_as_float(c[i]));
+            for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(a[i]);
 #pragma unroll
-            for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], fmaxf(__uint_as_float(a[i]), __uint_as_float(c[i])));
-            mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+            for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(a[i]));
+            mx = fmaxf(mx, fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])));
           }
           // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays exact
           // enough in 16 bits; the final O / l normalisation cancels the stale offset).  (-inf - -inf = NaN keeps m_run.)
@@ -453,8 +468,9 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // ---- item epilogue: O / l -> the 16-bit planes of the proj GEMM (and / or fp32).  The other three streams of the SM
       // keep the pipes busy while this one waits for its last P V.
       mbar_wait(pv_done(s), (t - 1) & 1);
-      if (warp_valid && row < S) {
+      if (warp_valid) {                 // warp-uniform: tcgen05.ld is .sync.aligned -- every lane runs it, only the stores are per row
         tc_fence_after();
+        const bool row_ok = row < S;
         const float inv = 1.0f / l_run;
         const AttnOut& o = p.out;
         const bool inA = row < o.split;
@@ -474,11 +490,11 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 #pragma unroll
             for (int q = 0; q < 8; ++q) y[q] = __uint_as_float(r0[c * 8 + q]) * inv;
             const int64_t oo = off + 32 * hh + c * 8;
-            if (of) {
+            if (of && row_ok) {
               *reinterpret_cast<float4*>(of + oo) = make_float4(y[0], y[1], y[2], y[3]);
               *reinterpret_cast<float4*>(of + oo + 4) = make_float4(y[4], y[5], y[6], y[7]);
             }
-            if (oh) {
+            if (oh && row_ok) {
               uint32_t hp[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) hp[q] = pack2_sat16(y[2 * q], y[2 * q + 1], FP16);
@@ -492,8 +508,6 @@ attention_tc6_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
             }
           }
         }
-      } else if (warp_valid) {
-        tc_fence_after();
       }
       // the O columns are overwritten by the first P V of the next item, which waits for a p_ready that this warp only
       // arrives at after the reads above (tcgen05.wait::ld inside the loop) -- no extra barrier needed
@@ -528,6 +542,14 @@ int launch_attention_tc6(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
     STK_CUDA(cudaFuncSetAttribute(attention_tc6_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     STK_CUDA(cudaFuncSetAttribute(attention_tc6_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_dev[dev] = true;
+    if (getenv("SELFTOK_DEBUG")) {
+      int occ = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, attention_tc6_kernel<true>, NUM_THREADS, SMEM_BYTES);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, attention_tc6_kernel<true>);
+      fprintf(stderr, "attention_tc6: %d resident CTAs per SM (%d registers, %d B dynamic smem, %zu B local)\n", occ, fa.numRegs, SMEM_BYTES,
+              (size_t)fa.localSizeBytes);
+    }
   }
   CUtensorMap mq, mkv;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)3 * H * HD;

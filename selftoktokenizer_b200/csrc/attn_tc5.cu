@@ -30,8 +30,6 @@
 #include <cuda.h>
 
 #include <algorithm>
-#include <type_traits>
-#include <stdlib.h>
 
 namespace stk {
 
@@ -42,10 +40,16 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 namespace {
 
 constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 4;
+// S buffers in TMEM: 2 = S double-buffered + O double-buffered by item parity (deferred item epilogue);
+//                    3 = S triple-buffered (Q K^T runs two tiles ahead of the softmax) + ONE O buffer (immediate epilogue)
+#ifndef SELFTOK_ATTN5_NSB
+#define SELFTOK_ATTN5_NSB 2
+#endif
+constexpr int NSB = SELFTOK_ATTN5_NSB;
 constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2;
 constexpr int SMEM_TILES = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES;            // 2 x 16 + 64 = 96 KiB (P lives in TMEM)
 constexpr int XCH_BYTES = 6 * BQ * 4;               // row-max exchange (2 parities x 2 halves) + partial-sum exchange (2 halves)
-constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 160 + XCH_BYTES;   // tiles + alignment slack + barriers + exchange
+constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 256 + XCH_BYTES;   // tiles + alignment slack + barriers + exchange
 constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O0 [128,192) | O1 [192,256); P_g overwrites half of S_g in place
 constexpr int NUM_THREADS = 64 + 8 * 32;        // TMA warp, MMA warp, 8 softmax warps
 constexpr float kRescaleThreshold = 8.0f;       // log2 units
@@ -191,27 +195,10 @@ __device__ __forceinline__ uint32_t pack2_16(float lo, float hi, bool fp16) {
   return r;
 }
 
-#ifdef SELFTOK_ATTN_TRACE
-// debug build only (profiles/mk_variant.sh with -DSELFTOK_ATTN_TRACE): per-event clock stamps of CTA 0, one private slot
-// list per warp (plain stores, no atomics: a returning atomic would put ~1000 cycles of latency into every stamp)
-__device__ unsigned long long g_trace[16][4096];
-#define TRACE_DECL int trace_i = 0
-#define TRACE(tag, g)                                                                                                   \
-  do {                                                                                                                  \
-    if (lane == 0 && blockIdx.x == 0 && trace_i < 4096)                                                                 \
-      g_trace[warp][trace_i++] = ((unsigned long long)(tag) << 56) | ((unsigned long long)(warp & 0xff) << 48) |        \
-                                 ((unsigned long long)((g) & 0xffff) << 32) | (unsigned long long)(clock64() & 0xffffffffu); \
-  } while (0)
-#else
-#define TRACE_DECL
-#define TRACE(tag, g) do { } while (0)
-#endif
-
 struct Attn5Params {
   AttnOut out;
   int B, S, H, ctx_rows, ctx_keys, fp16;
   float scale_log2e;
-  int rot;                 // per-round rotation of the item -> CTA map (load balance; see item_of)
 };
 
 template <bool FP16>
@@ -225,17 +212,20 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   // every per-tile barrier exists twice (tile parity) so that no waiter can be lapped by two phases
   auto q_full = [&](int qb) { return bars + 8u * qb; };
   auto q_empty = [&](int qb) { return bars + 16 + 8u * qb; };
-  auto p_ready = [&](int pb) { return bars + 32 + 8u * pb; };
-  auto pv_done = [&](int pb) { return bars + 48 + 8u * pb; };
-  auto s_full = [&](int sb) { return bars + 64 + 8u * sb; };
-  auto kv_full = [&](int st) { return bars + 80 + 8u * st; };
-  auto kv_empty = [&](int st) { return bars + 80 + 8u * KV_STAGES + 8u * st; };
-  const uint32_t tmem_slot = bars + 80 + 16u * KV_STAGES;
+  auto p_ready = [&](int pb) { return bars + 32 + 8u * pb; };               // per S buffer (up to 3)
+  auto pv_done = [&](int pb) { return bars + 56 + 8u * pb; };
+  auto s_full = [&](int sb) { return bars + 80 + 8u * sb; };
+  auto kv_full = [&](int st) { return bars + 104 + 8u * st; };
+  auto kv_empty = [&](int st) { return bars + 104 + 8u * KV_STAGES + 8u * st; };
+  const uint32_t tmem_slot = bars + 104 + 16u * KV_STAGES;
+  // tile g lives in S buffer SB(g), phase SPH(g) of that buffer's barriers; item n accumulates in O buffer OB(n)
+  auto SB = [](int g) { return g % NSB; };
+  auto SPH = [](int g) { return (uint32_t)((g / NSB) & 1); };
+  auto OB = [](int n) { return NSB == 2 ? (n & 1) : 0; };
   const uint32_t xch_s = tmem_slot + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  TRACE_DECL;
   const int S = p.S;
   // persistent CTA: work items (image b, head h, query tile qt), qt fastest, so that the CTAs running side by side share
   // the K / V tiles of one (b, h) in L2.  All roles walk the same item sequence with a CTA-global tile counter g that
@@ -247,22 +237,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const int kmax_cta = ((qt + 1) * BQ <= p.ctx_rows) ? p.ctx_keys : S;  // every row of the tile is a context row
     return (kmax_cta + BKV - 1) / BKV;
   };
-  // The CTA's n-th item: round n covers items [n G, (n + 1) G), and the CTA -> item map inside a round is rotated by
-  // n * rot.  Items differ in cost (the last query tile of a ragged S has idle softmax quarters, renderer context tiles see
-  // fewer keys), and with a fixed stride G a CTA would meet the same query tile every round whenever G % nq == 0; the host
-  // picks rot so that the query-tile index walks through all residues.  Neighbouring CTAs still hold neighbouring items.
-  const int G = (int)gridDim.x;
-  auto item_of = [&](int n) -> int {
-    const long long base = (long long)n * G;
-    if (base >= n_items) return -1;
-    const int it = (int)base + (int)(((long long)blockIdx.x + (long long)n * p.rot) % G);
-    return it < n_items ? it : -1;
-  };
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1); mbar_init(s_full(i), 1); mbar_init(p_ready(i), 8); mbar_init(pv_done(i), 1);
-    }
+    for (int i = 0; i < 2; ++i) { mbar_init(q_full(i), 1); mbar_init(q_empty(i), 1); }
+    for (int i = 0; i < NSB; ++i) { mbar_init(s_full(i), 1); mbar_init(p_ready(i), 8); mbar_init(pv_done(i), 1); }
     for (int st = 0; st < KV_STAGES; ++st) { mbar_init(kv_full(st), 1); mbar_init(kv_empty(st), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -277,7 +255,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   // S buffer sb at s_tmem0 + 64 * sb; O buffer (item parity) ob at o_tmem0 + 64 * ob.  P_g (16-bit pairs, two keys per
   // column) replaces S_g in place: the thread that loaded S columns [32 half, 32 half + 32) writes its 32 keys into columns
   // [32 half, 32 half + 16) -- nobody else reads those, and Q K^T of tile g+2 (same buffer) is issued after P V of tile g.
-  const uint32_t s_tmem0 = tmem_base, o_tmem0 = tmem_base + 128;
+  const uint32_t s_tmem0 = tmem_base, o_tmem0 = tmem_base + 64 * NSB;
 
   if (warp == 0) {
     // =========================================================== TMA producer
@@ -290,12 +268,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tma_load_2d(q_s + qb * Q_BYTES, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
       };
       int g = 0, n = 0;
-      if (item_of(0) >= 0) load_q(item_of(0), 0);
-      for (int item = item_of(0); item >= 0; item = item_of(++n)) {
+      if ((int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
         const int row0 = b * S;                                         // first row of this image in the [B*S, 3*H*64] matrix
         const int n_tiles = item_tiles(qt);
-        if (item_of(n + 1) >= 0) load_q(item_of(n + 1), n + 1);         // next item's Q, one item ahead
+        if (item + (int)gridDim.x < n_items) load_q(item + gridDim.x, n + 1);   // next item's Q, one item ahead
         for (int j = 0; j < n_tiles; ++j, ++g) {
           const int st = g % KV_STAGES;
           const uint32_t ph = (g / KV_STAGES) & 1;
@@ -312,45 +290,51 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (lane == 0) {
       const uint32_t idesc_qk = make_idesc(BQ, BKV, FP16 ? 1 : 0, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
       const uint32_t idesc_pv = make_idesc(BQ, HD, FP16 ? 1 : 0, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
-      // S[gg & 1] = Q_n K_gg^T for the tile with CTA-global index gg of local item n; `last` releases the Q buffer
-      auto issue_qk = [&](int n, int gg, bool first, bool last) {
-        const int qb = n & 1, st = gg % KV_STAGES;
-        if (first) mbar_wait(q_full(qb), (n >> 1) & 1);
-        mbar_wait(kv_full(st), (gg / KV_STAGES) & 1);
+      // Two cursors walk the same (item, tile) sequence: the Q K^T cursor runs NSB - 1 tiles ahead of the P V cursor (across
+      // item boundaries), so S_{g + NSB - 1} is being computed while the softmax warps work on S_g.
+      struct Cur { int item, n, j, nt; };
+      auto cur_first = [&]() {
+        Cur c{(int)blockIdx.x, 0, 0, 0};
+        c.nt = c.item < n_items ? item_tiles(c.item % nq) : 0;
+        return c;
+      };
+      auto cur_next = [&](Cur& c) {
+        if (++c.j == c.nt) {
+          c.item += gridDim.x; ++c.n; c.j = 0;
+          c.nt = c.item < n_items ? item_tiles(c.item % nq) : 0;
+        }
+      };
+      Cur cq = cur_first();
+      int gq = 0;
+      auto issue_qk = [&]() {                                          // S[SB(gq)] = Q K_gq^T, then advance the cursor
+        const int qb = cq.n & 1, st = gq % KV_STAGES;
+        if (cq.j == 0) mbar_wait(q_full(qb), (cq.n >> 1) & 1);
+        mbar_wait(kv_full(st), (gq / KV_STAGES) & 1);
         tc_fence_after();
         const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES, qs = q_s + qb * Q_BYTES;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)                                // K dimension = head dim: 32 B per k-step inside the row
-          tc_mma_f16(s_tmem0 + 64 * (gg & 1), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-        tc_commit(s_full(gg & 1));
-        if (last) tc_commit(q_empty(qb));
-        TRACE(12, gg);
+          tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+        tc_commit(s_full(SB(gq)));
+        if (cq.j == cq.nt - 1) tc_commit(q_empty(qb));                  // last tile of the item: Q buffer reusable
+        cur_next(cq);
+        ++gq;
       };
-      int g = 0, n = 0;
-      if (item_of(0) >= 0) {
-        const int nt0 = item_tiles(item_of(0) % nq);
-        issue_qk(0, 0, true, nt0 == 1);
-      }
-      for (int item = item_of(0); item >= 0; item = item_of(++n)) {
-        const int n_tiles = item_tiles(item % nq);
-        const int next = item_of(n + 1);
-        for (int j = 0; j < n_tiles; ++j, ++g) {
-          // look-ahead Q K^T (overlaps the softmax of tile g: S is double-buffered); crosses into the next item at the end
-          if (j + 1 < n_tiles) issue_qk(n, g + 1, false, j + 2 == n_tiles);
-          else if (next >= 0) issue_qk(n + 1, g + 1, true, item_tiles(next % nq) == 1);
-          const int st = g % KV_STAGES;
-          const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
-          mbar_wait(p_ready(g & 1), (g >> 1) & 1);                       // P_g in TMEM, O rescaled (or read out), S[g & 1] consumed
-          TRACE(10, g);
-          tc_fence_after();
+      for (int i = 0; i < NSB - 1 && cq.item < n_items; ++i) issue_qk();
+      Cur cp = cur_first();
+      for (int g = 0; cp.item < n_items; ++g) {
+        if (cq.item < n_items) issue_qk();                               // look-ahead Q K^T (its S buffer was freed by P V_{g-1})
+        const int st = g % KV_STAGES;
+        const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
+        mbar_wait(p_ready(SB(g)), SPH(g));                               // P_g in TMEM, O rescaled (or read out), S[SB(g)] consumed
+        tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)                             // K dimension = keys: 16 keys = 2 atoms of 8 key rows
-            tc_mma_f16_ts(o_tmem0 + 64 * (n & 1), s_tmem0 + 64 * (g & 1) + 32 * (k >> 1) + 8 * (k & 1), make_smem_desc(vs + k * 2048),
-                          idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-          tc_commit(kv_empty(st));                                       // K/V stage reusable once QK_g and PV_g retire
-          tc_commit(pv_done(g & 1));                                     // O[n & 1] holds tiles 0..j of the item
-          TRACE(11, g);
-        }
+        for (int k = 0; k < BKV / 16; ++k)                               // K dimension = keys: 16 keys = 2 atoms of 8 key rows
+          tc_mma_f16_ts(o_tmem0 + 64 * OB(cp.n), s_tmem0 + 64 * SB(g) + 32 * (k >> 1) + 8 * (k & 1), make_smem_desc(vs + k * 2048),
+                        idesc_pv, (cp.j > 0 || k > 0) ? 1u : 0u);
+        tc_commit(kv_empty(st));                                         // K/V stage reusable once QK_g and PV_g retire
+        tc_commit(pv_done(SB(g)));                                       // O holds tiles 0..j of the item
+        cur_next(cp);
       }
     }
   } else {
@@ -370,10 +354,10 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     auto epilogue = [&](int item, int n, int g_last, float l_run) {
       const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
       const int row = qt * BQ + rl;
-      mbar_wait(pv_done(g_last & 1), (g_last >> 1) & 1);
+      mbar_wait(pv_done(SB(g_last)), SPH(g_last));
       tc_fence_after();
       uint32_t r0[32];
-      tmem_ld32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
+      tmem_ld32(o_tmem0 + 64 * OB(n) + 32 * half + lane_addr, r0);
       tmem_ld_wait();
       if (row < S) {
         const float inv = 1.0f / l_run;
@@ -410,137 +394,90 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     };
     int g = 0, n = 0, pend_item = -1, pend_g = 0;
     float pend_l = 1.f;
-    for (int item = item_of(0); item >= 0; item = item_of(++n)) {
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
       const int qt = item % nq;
       const int n_tiles = item_tiles(qt);
       const int row = qt * BQ + rl;
       const int kmax = (row < p.ctx_rows) ? p.ctx_keys : S;
-      // Warp-uniform facts about this warp's 32 rows.  A quarter that lies entirely past the end of the sequence (the last
-      // query tile of a ragged S: S runs from 276 to 768 over the sampler schedule) does no softmax work at all -- its P / O
-      // rows are never stored -- it only keeps pace with the barriers.
-      const bool warp_valid = qt * BQ + quarter * 32 < S;
       float m_run = -INFINITY, l_part = 0.f;
       for (int j = 0; j < n_tiles; ++j, ++g) {
-        mbar_wait(s_full(g & 1), (g >> 1) & 1);
-        TRACE(1, g);
-        if (warp_valid) {
-          tc_fence_after();
-          uint32_t r0[32];
-          tmem_ld32(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, r0);
-          tmem_ld_wait();
-          TRACE(2, g);
-          const int k0 = j * BKV + 32 * half;
-          if (k0 + 32 > kmax) {                                           // tile straddles this row's key limit
+        mbar_wait(s_full(SB(g)), SPH(g));
+        tc_fence_after();
+        uint32_t r0[32];
+        tmem_ld32(s_tmem0 + 64 * SB(g) + 32 * half + lane_addr, r0);
+        tmem_ld_wait();
+        const int k0 = j * BKV + 32 * half;
+        if (k0 + 32 > kmax) {                                             // tile straddles this row's key limit
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (k0 + i >= kmax) r0[i] = 0xff800000u;                    // -inf
-          }
-          // P = 2^(s * scale - m) for this thread's 32 keys as 16 packed 16-bit columns + their fp32 sum.  Scale / subtract and
-          // the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2), ex2.approx on the MUFU pipe, one cvt per pair.
-          // With TRACK_MAX the half-row maximum of the raw scores is folded into the same loop (one 3-input max per pair), so
-          // that its instructions sit between the MUFU ops in program order and issue under their latency.
-          float mloc[4];
-          auto exps = [&](float nsub, uint32_t (&w)[16], auto track_max) -> float {
-            constexpr bool TRACK_MAX = decltype(track_max)::value;
-            float rsp[4] = {0.f, 0.f, 0.f, 0.f};
-            if (TRACK_MAX) {
-#pragma unroll
-              for (int i = 0; i < 4; ++i) mloc[i] = -INFINITY;
-            }
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              float x0, x1;
-              scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
-#ifdef SELFTOK_ABL_NO_EXP
-              const float e0 = x0, e1 = x1;
-#else
-              const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
-#endif
-              if (TRACK_MAX) mloc[q & 3] = fmaxf(mloc[q & 3], fmaxf(__uint_as_float(r0[2 * q]), __uint_as_float(r0[2 * q + 1])));
-              add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
-              w[q] = pack2_16(e0, e1, FP16);
-            }
-            return (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
-          };
-          // the half-row maxima of the two threads of a row meet in shared memory (double-buffered by tile parity: one
-          // 64-thread named barrier per tile)
-          auto exchange_max = [&](float mx) -> float {
-#ifdef SELFTOK_ABL_NO_MAX
-            return 0.f;
-#else
-            xch[((g & 1) * 2 + half) * BQ + rl] = mx;
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            return fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
-#endif
-          };
-          uint32_t w[16];
-          float rs = 0.f;
-          // SPECULATION: with the lazy rescale the reference maximum m_run almost never moves after the first tile of an item,
-          // so the exponentials are issued against m_run straight after the TMEM load, BEFORE the tile maximum is known; the
-          // max tree, the half-row exchange through shared memory and its named barrier then run under the MUFU latency
-          // instead of in front of it.  Only if some row of the warp did move its maximum (first tile; score jumps > 2^8)
-          // is the tile recomputed against the new maximum -- S is still in registers (P is stored after the check).
-#ifdef SELFTOK_ATTN_NO_SPEC
-          const bool spec = false;
-#else
-          const bool spec = j > 0 && __all_sync(0xffffffffu, m_run != -INFINITY);
-#endif
-          float mx;
-          if (spec) {
-            rs = exps(-m_run, w, std::true_type());
-            mx = exchange_max(fmaxf(fmaxf(mloc[0], mloc[1]), fmaxf(mloc[2], mloc[3])));
-          } else {
-            float mp[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
-#pragma unroll
-            for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
-            mx = exchange_max(fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3])));
-          }
-          // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays
-          // exact enough in 16 bits and the final O / l normalisation cancels the stale offset), so the O correction pass and
-          // its wait on the previous P V are rare instead of per tile.  (-inf - -inf = NaN keeps m_run: comparison is false.)
-          float m_new = fmaxf(m_run, mx * p.scale_log2e);
-          if (m_new - m_run <= kRescaleThreshold) m_new = m_run;
-          float corr = 1.f;
-          if (!spec || __any_sync(0xffffffffu, m_new != m_run)) {
-            const float sub = (m_new == -INFINITY) ? 0.f : m_new;
-            corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
-            rs = exps(-sub, w, std::false_type());
-          }
-          TRACE(3, g);
-          // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
-          tmem_st16(s_tmem0 + 64 * (g & 1) + 32 * half + lane_addr, w);
-          l_part = l_part * corr + rs;
-          m_run = m_new;
-          // rescale this thread's 32 output dims only when some row of the warp moved its maximum
-          if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
-            mbar_wait(pv_done((g - 1) & 1), ((g - 1) >> 1) & 1);            // PV of the previous tile retired: O is stable
-            tc_fence_after();
-            tmem_ld32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
-            tmem_st32(o_tmem0 + 64 * (n & 1) + 32 * half + lane_addr, r0);
-          }
-          tmem_st_wait();                                                   // P (and the rescaled O) are in TMEM
-          TRACE(4, g);
+          for (int i = 0; i < 32; ++i)
+            if (k0 + i >= kmax) r0[i] = 0xff800000u;                      // -inf
         }
+        float mx;
+        {
+          float mp[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mp[i] = __uint_as_float(r0[i]);
+#pragma unroll
+          for (int i = 4; i < 32; ++i) mp[i & 3] = fmaxf(mp[i & 3], __uint_as_float(r0[i]));
+          mx = fmaxf(fmaxf(mp[0], mp[1]), fmaxf(mp[2], mp[3]));
+        }
+        // exchange the half-row maxima (double-buffered by tile parity: no second barrier needed)
+        xch[((g & 1) * 2 + half) * BQ + rl] = mx;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        mx = fmaxf(mx, xch[((g & 1) * 2 + (half ^ 1)) * BQ + rl]);
+        // lazy rescale: the reference maximum only moves when the running maximum grew by more than 2^8 (P <= 256 stays
+        // exact enough in 16 bits and the final O / l normalisation cancels the stale offset), so the O correction pass and
+        // its wait on the previous P V are rare instead of per tile.  (-inf - -inf = NaN keeps m_run: comparison is false.)
+        float m_new = fmaxf(m_run, mx * p.scale_log2e);
+        if (m_new - m_run <= kRescaleThreshold) m_new = m_run;
+        const float sub = (m_new == -INFINITY) ? 0.f : m_new;
+        const float corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
+        // scale / subtract and the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2): the softmax warps are
+        // co-limited by issue slots and the MUFU pipe, so every instruction saved around the 32 ex2 counts
+        uint32_t w[16];
+        float rsp[4] = {0.f, 0.f, 0.f, 0.f};
+        const float nsub = -sub;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          float x0, x1;
+          scale_sub2(r0[2 * q], r0[2 * q + 1], p.scale_log2e, nsub, x0, x1);
+          const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+          add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
+          w[q] = pack2_16(e0, e1, FP16);
+        }
+        const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
+        // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
+        tmem_st16(s_tmem0 + 64 * SB(g) + 32 * half + lane_addr, w);
+        l_part = l_part * corr + rs;
+        m_run = m_new;
+        // rescale this thread's 32 output dims only when some row of the warp moved its maximum
+        if (j > 0 && !__all_sync(0xffffffffu, corr == 1.0f)) {
+          mbar_wait(pv_done(SB(g - 1)), SPH(g - 1));                      // PV of the previous tile retired: O is stable
+          tc_fence_after();
+          tmem_ld32(o_tmem0 + 64 * OB(n) + 32 * half + lane_addr, r0);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(__uint_as_float(r0[i]) * corr);
+          tmem_st32(o_tmem0 + 64 * OB(n) + 32 * half + lane_addr, r0);
+        }
+        tmem_st_wait();                                                   // P (and the rescaled O) are in TMEM
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready(g & 1));
-        if (j == 0 && pend_item >= 0) {
+        if (lane == 0) mbar_arrive(p_ready(SB(g)));
+        if (NSB == 2 && j == 0 && pend_item >= 0) {
           epilogue(pend_item, n - 1, pend_g, pend_l);
           pend_item = -1;
         }
       }
       // ---- item end: combine the partial row sums now, leave the read-out of O for after the next item's first tile
-      if (warp_valid) {
-        xch[(4 + half) * BQ + rl] = l_part;
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        pend_l = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
-        pend_item = item;
-        pend_g = g - 1;
+      xch[(4 + half) * BQ + rl] = l_part;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      pend_l = l_part + xch[(4 + (half ^ 1)) * BQ + rl];
+      pend_item = item;
+      pend_g = g - 1;
+      if (NSB != 2) {                   // one O buffer: read it out now (the next item's first P V waits for our next p_ready)
+        epilogue(pend_item, n, pend_g, pend_l);
+        pend_item = -1;
       }
     }
     if (pend_item >= 0) epilogue(pend_item, n - 1, pend_g, pend_l);
@@ -556,15 +493,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
 int g_num_sms_dev[64];
 bool g_attr_dev[64];       // cudaFuncSetAttribute is per device: one handle per GPU may live in the same process
 
-int gcd_i(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
-
 }  // namespace
 
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16) {
   STK_CHECK(qkv16 && B > 0 && S > 0 && H > 0, -1, "attention_tc5: bad arguments");
   STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
-  STK_CHECK(ctx_keys <= S && ctx_rows <= S, -1, "attention_tc5: context limits exceed the sequence");
+  STK_CHECK(ctx_keys <= S && ctx_rows <= S && ctx_keys >= 0 && ctx_rows >= 0, -1, "attention_tc5: context limits exceed the sequence");
   STK_TRY(gemm_tc_init());
   int dev = 0;
   STK_CUDA(cudaGetDevice(&dev));
@@ -575,32 +510,19 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
     STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     g_attr_dev[dev] = true;
   }
+  const int g_num_sms = g_num_sms_dev[dev];
   CUtensorMap mq, mkv;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)3 * H * HD;
   STK_TRY(make_tensor_map_2d(&mq, qkv16, rows, cols, BQ, HD, fp16));
   STK_TRY(make_tensor_map_2d(&mkv, qkv16, rows, cols, BKV, HD, fp16));
-  const int nq = (S + BQ - 1) / BQ;
-  const int n_items = nq * H * B;
-  const int grid = std::min(n_items, 2 * g_num_sms_dev[dev]);      // persistent: two CTAs per SM walk the item list
-  int rot = 0;                                                     // smallest rotation that makes the query-tile walk full-period
-  while (gcd_i((grid + rot) % nq == 0 ? nq : (grid + rot) % nq, nq) != 1 && rot < nq) ++rot;
-  Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f, rot};
+  Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
+  const int n_items = ((S + BQ - 1) / BQ) * H * B;
+  dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
   if (fp16) attention_tc5_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   else attention_tc5_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;
 }
-
-#ifdef SELFTOK_ATTN_TRACE
-extern "C" __attribute__((visibility("default"))) int selftok_dbg_attn_trace(unsigned long long* out_host, int max_n) {
-  cudaDeviceSynchronize();
-  if (max_n < 16 * 4096) return -1;
-  cudaMemcpyFromSymbol(out_host, g_trace, sizeof(unsigned long long) * 16 * 4096);
-  static unsigned long long zeros[16 * 4096];
-  cudaMemcpyToSymbol(g_trace, zeros, sizeof(zeros));
-  return 16 * 4096;
-}
-#endif
 
 }  // namespace stk

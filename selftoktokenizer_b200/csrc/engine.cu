@@ -61,7 +61,6 @@ struct selftok_engine {
   bool finalized = false;
   bool use_graph = true;
   bool attn_tcgen05 = true;             // single-pass modes: tcgen05/TMEM attention (SELFTOK_ATTN=mma selects the mma.sync kernel)
-  int attn_gen = 6;                     // 6: four-stream kernel (attn_tc6.cu); 5: one tile per CTA (attn_tc5.cu; SELFTOK_ATTN=tc5)
   std::unordered_map<std::string, Tensor> w;
   std::unordered_map<std::string, WPack> wp;
   std::vector<void*> allocs;            // tables + packed weights
@@ -221,7 +220,6 @@ extern "C" __attribute__((visibility("default"))) int selftok_create(const selft
   {
     const char* v = getenv("SELFTOK_ATTN");
     if (v && std::string(v) == "mma") e->attn_tcgen05 = false;
-    if (v && std::string(v) == "tc5") e->attn_gen = 5;
   }
   if (tc_mode(e)) {
     int st = gemm_tc_init();
@@ -711,8 +709,7 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       ao.fp16 = fp16;
       const int ctx_rows = ctx_self ? Kc : 0, ctx_keys = ctx_self ? Kc : 0;
       if (nsplit(e) == 1 && e->attn_tcgen05)
-        PROF(PC_ATTN, e->attn_gen == 6 ? launch_attention_tc6(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16)
-                                       : launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16));
+        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16));
       else
         PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, fp16));
       // post_attention (mmdit.py:485-496); the pre_only context block of the last layer stops here
@@ -759,8 +756,7 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
       ao.fp16 = is_fp16(e);
       if (nsplit(e) == 1 && e->attn_tcgen05)
-        PROF(PC_ATTN, e->attn_gen == 6 ? launch_attention_tc6(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e))
-                                       : launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e)));
+        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e)));
       else
         PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, is_fp16(e)));
     }
@@ -1032,11 +1028,9 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_f32(co
 
 extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(const float* qkv, float* out, int B, int S, int H, int ns, int ctx_rows, int ctx_keys,
                                       void* stream) {
-  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3 || ns == 10 || ns == 11 || ns == 20 || ns == 21), SELFTOK_ERR_BAD_ARG,
-            "selftok_k_attention_tc: bad argument");
-  const bool tc6 = ns >= 20;                    // 20 / 21: four-stream tcgen05 kernel (attn_tc6.cu), IEEE half / bf16
-  const bool tc5 = ns >= 10 && !tc6;            // 10 / 11: one-tile-per-CTA tcgen05 kernel (attn_tc5.cu), IEEE half / bf16
-  const int fp16 = ns == 0 || ns == 10 || ns == 20;
+  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3 || ns == 10 || ns == 11), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
+  const bool tc5 = ns >= 10;                    // 10: tcgen05 kernel, IEEE half; 11: tcgen05 kernel, bf16
+  const int fp16 = ns == 0 || ns == 10;
   if (ns != 3) ns = 1;
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n = (int64_t)B * S * 3 * H * 64;
@@ -1046,8 +1040,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(con
   int st = launch_split_bf16(qkv, qh, ql, n, s, fp16);
   AttnOut ao;
   ao.f32_a = out; ao.split = S; ao.ld = (int64_t)H * 64;
-  if (!st && tc6) st = launch_attention_tc6(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
-  else if (!st && tc5) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
+  if (!st && tc5) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
   else if (!st) st = launch_attention_tc(qh, ql, B, S, H, ns, ctx_rows, ctx_keys, ao, s, fp16);
   cudaStreamSynchronize(s);
   cudaFree(qh);

@@ -114,8 +114,4 @@ int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
                          cudaStream_t s, int fp16);
 
-// four-stream tcgen05 / TMEM attention (attn_tc6.cu): two query tiles per CTA sharing K / V, one thread per query row
-int launch_attention_tc6(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
-                         cudaStream_t s, int fp16);
-
 }  // namespace stk
