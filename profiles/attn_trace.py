@@ -22,7 +22,7 @@ dev = torch.device("cuda:0")
 lib = capi.load_library()
 dump = lib.selftok_dbg_attn_trace6 if GEN == 6 else lib.selftok_dbg_attn_trace
 dump.argtypes = [C.c_void_p, C.c_int]
-NS = 20 if GEN == 6 else 10
+NS = 0          # IEEE-half single pass
 B, H = 16, 24
 qkv = torch.randn(B, S, 3, H, 64, device=dev)
 buf = (C.c_ulonglong * 65536)()

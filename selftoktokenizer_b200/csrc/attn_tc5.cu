@@ -39,7 +39,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* ptr, uint64_t rows, uint64_
 
 namespace {
 
-constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 4;
+constexpr int HD = 64, BQ = 128, BKV = 64;
 // S buffers in TMEM: 2 = S double-buffered + O double-buffered by item parity (deferred item epilogue);
 //                    3 = S triple-buffered (Q K^T runs two tiles ahead of the softmax) + ONE O buffer (immediate epilogue)
 #ifndef SELFTOK_ATTN5_NSB
@@ -47,9 +47,20 @@ constexpr int HD = 64, BQ = 128, BKV = 64, KV_STAGES = 4;
 #endif
 constexpr int NSB = SELFTOK_ATTN5_NSB;
 constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2;
-constexpr int SMEM_TILES = 2 * Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES;            // 2 x 16 + 64 = 96 KiB (P lives in TMEM)
 constexpr int XCH_BYTES = 6 * BQ * 4;               // row-max exchange (2 parities x 2 halves) + partial-sum exchange (2 halves)
-constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 256 + XCH_BYTES;   // tiles + alignment slack + barriers + exchange
+// NSPLIT == 1: single-pass 16-bit operands, 2 CTAs per SM.  NSPLIT == 3 ("bf16x3", fp32-faithful): every product is
+// hi*hi + hi*lo + lo*hi of bf16 planes accumulated into the same TMEM tile -- Q, K, V arrive as hi and lo planes (twice the
+// shared memory: one CTA per SM, three K/V stages), P is split in registers and its lo half goes into the S columns the hi
+// half leaves free.
+template <int NSPLIT> struct A5 {
+  static constexpr int PL = NSPLIT == 3 ? 2 : 1;                        // operand planes
+  static constexpr int KV_STAGES = NSPLIT == 3 ? 3 : 4;
+  static constexpr int Q_STAGE = PL * Q_BYTES;                          // [hi | lo]
+  static constexpr int KV_STAGE = PL * 2 * KV_TILE_BYTES;               // [K hi | V hi | K lo | V lo]
+  static constexpr int SMEM_TILES = 2 * Q_STAGE + KV_STAGES * KV_STAGE; // 96 KiB / 160 KiB (P lives in TMEM)
+  static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 256 + XCH_BYTES;   // tiles + alignment slack + barriers + exchange
+  static constexpr int MIN_CTAS = NSPLIT == 3 ? 1 : 2;
+};
 constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O0 [128,192) | O1 [192,256); P_g overwrites half of S_g in place
 constexpr int NUM_THREADS = 64 + 8 * 32;        // TMA warp, MMA warp, 8 softmax warps
 constexpr float kRescaleThreshold = 8.0f;       // log2 units
@@ -201,14 +212,18 @@ struct Attn5Params {
   float scale_log2e;
 };
 
-template <bool FP16>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
-attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, const Attn5Params p) {
+template <bool FP16, int NSPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, A5<NSPLIT>::MIN_CTAS)
+attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
+                     const __grid_constant__ CUtensorMap map_q_lo, const __grid_constant__ CUtensorMap map_kv_lo, const Attn5Params p) {
+  static_assert(NSPLIT == 1 || (NSPLIT == 3 && !FP16), "split mode uses bf16 planes");
+  using C = A5<NSPLIT>;
+  constexpr int KV_STAGES = C::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t q_s = base;                                  // Q buffer qb at q_s + qb * Q_BYTES
-  const uint32_t kv_s = base + 2 * Q_BYTES;                   // stage st: K at kv_s + st*2*KV_TILE_BYTES, V right after
-  const uint32_t bars = kv_s + KV_STAGES * 2 * KV_TILE_BYTES;
+  const uint32_t q_s = base;                                  // Q buffer qb at q_s + qb * Q_STAGE (hi plane, lo plane)
+  const uint32_t kv_s = base + 2 * C::Q_STAGE;                // stage st at kv_s + st * KV_STAGE: K hi, V hi (, K lo, V lo)
+  const uint32_t bars = kv_s + KV_STAGES * C::KV_STAGE;
   // every per-tile barrier exists twice (tile parity) so that no waiter can be lapped by two phases
   auto q_full = [&](int qb) { return bars + 8u * qb; };
   auto q_empty = [&](int qb) { return bars + 16 + 8u * qb; };
@@ -264,8 +279,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
         const int qb = n & 1;
         mbar_wait(q_empty(qb), ((n >> 1) & 1) ^ 1);
-        mbar_expect_tx(q_full(qb), Q_BYTES);
-        tma_load_2d(q_s + qb * Q_BYTES, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
+        mbar_expect_tx(q_full(qb), C::Q_STAGE);
+        tma_load_2d(q_s + qb * C::Q_STAGE, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
+        if (NSPLIT == 3) tma_load_2d(q_s + qb * C::Q_STAGE + Q_BYTES, &map_q_lo, q_full(qb), h * HD, b * S + qt * BQ);
       };
       int g = 0, n = 0;
       if ((int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
@@ -278,10 +294,14 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const int st = g % KV_STAGES;
           const uint32_t ph = (g / KV_STAGES) & 1;
           mbar_wait(kv_empty(st), ph ^ 1);
-          const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES;
-          mbar_expect_tx(kv_full(st), 2 * KV_TILE_BYTES);
+          const uint32_t ks = kv_s + st * C::KV_STAGE;
+          mbar_expect_tx(kv_full(st), C::KV_STAGE);
           tma_load_2d(ks, &map_kv, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
           tma_load_2d(ks + KV_TILE_BYTES, &map_kv, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+          if (NSPLIT == 3) {
+            tma_load_2d(ks + 2 * KV_TILE_BYTES, &map_kv_lo, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
+            tma_load_2d(ks + 3 * KV_TILE_BYTES, &map_kv_lo, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+          }
         }
       }
     }
@@ -311,10 +331,15 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (cq.j == 0) mbar_wait(q_full(qb), (cq.n >> 1) & 1);
         mbar_wait(kv_full(st), (gq / KV_STAGES) & 1);
         tc_fence_after();
-        const uint32_t ks = kv_s + st * 2 * KV_TILE_BYTES, qs = q_s + qb * Q_BYTES;
+        const uint32_t ks = kv_s + st * C::KV_STAGE, qs = q_s + qb * C::Q_STAGE;
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)                                // K dimension = head dim: 32 B per k-step inside the row
+        for (int k = 0; k < HD / 16; ++k) {                              // K dimension = head dim: 32 B per k-step inside the row
           tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+          if (NSPLIT == 3) {                                             // + Q_hi K_lo^T + Q_lo K_hi^T
+            tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + 2 * KV_TILE_BYTES + k * 32), idesc_qk, 1u);
+            tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + Q_BYTES + k * 32), make_smem_desc(ks + k * 32), idesc_qk, 1u);
+          }
+        }
         tc_commit(s_full(SB(gq)));
         if (cq.j == cq.nt - 1) tc_commit(q_empty(qb));                  // last tile of the item: Q buffer reusable
         cur_next(cq);
@@ -325,13 +350,18 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       for (int g = 0; cp.item < n_items; ++g) {
         if (cq.item < n_items) issue_qk();                               // look-ahead Q K^T (its S buffer was freed by P V_{g-1})
         const int st = g % KV_STAGES;
-        const uint32_t vs = kv_s + st * 2 * KV_TILE_BYTES + KV_TILE_BYTES;
+        const uint32_t vs = kv_s + st * C::KV_STAGE + KV_TILE_BYTES;
         mbar_wait(p_ready(SB(g)), SPH(g));                               // P_g in TMEM, O rescaled (or read out), S[SB(g)] consumed
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k)                               // K dimension = keys: 16 keys = 2 atoms of 8 key rows
-          tc_mma_f16_ts(o_tmem0 + 64 * OB(cp.n), s_tmem0 + 64 * SB(g) + 32 * (k >> 1) + 8 * (k & 1), make_smem_desc(vs + k * 2048),
-                        idesc_pv, (cp.j > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < BKV / 16; ++k) {                             // K dimension = keys: 16 keys = 2 atoms of 8 key rows
+          const uint32_t pa = s_tmem0 + 64 * SB(g) + 32 * (k >> 1) + 8 * (k & 1);      // P hi; P lo 16 columns further
+          tc_mma_f16_ts(o_tmem0 + 64 * OB(cp.n), pa, make_smem_desc(vs + k * 2048), idesc_pv, (cp.j > 0 || k > 0) ? 1u : 0u);
+          if (NSPLIT == 3) {                                             // + P_hi V_lo + P_lo V_hi
+            tc_mma_f16_ts(o_tmem0 + 64 * OB(cp.n), pa, make_smem_desc(vs + 2 * KV_TILE_BYTES + k * 2048), idesc_pv, 1u);
+            tc_mma_f16_ts(o_tmem0 + 64 * OB(cp.n), pa + 16, make_smem_desc(vs + k * 2048), idesc_pv, 1u);
+          }
+        }
         tc_commit(kv_empty(st));                                         // K/V stage reusable once QK_g and PV_g retire
         tc_commit(pv_done(SB(g)));                                       // O holds tiles 0..j of the item
         cur_next(cp);
@@ -434,7 +464,7 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         const float corr = (m_new == m_run || m_new == -INFINITY) ? 1.f : ex2_approx(m_run - m_new);
         // scale / subtract and the row sum run on the packed fp32 pipe (two keys per FFMA2 / FADD2): the softmax warps are
         // co-limited by issue slots and the MUFU pipe, so every instruction saved around the 32 ex2 counts
-        uint32_t w[16];
+        uint32_t w[16], wl[16];
         float rsp[4] = {0.f, 0.f, 0.f, 0.f};
         const float nsub = -sub;
 #pragma unroll
@@ -444,10 +474,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
           add2(rsp[2 * (q & 1)], rsp[2 * (q & 1) + 1], e0, e1);
           w[q] = pack2_16(e0, e1, FP16);
+          if (NSPLIT == 3) wl[q] = pack2_resid_bf16(e0, e1, w[q]);          // lo plane: rn(p - rn_bf16(p))
         }
         const float rs = (rsp[0] + rsp[1]) + (rsp[2] + rsp[3]);
         // this thread's 32 keys = 16 packed columns of row rl (TMEM lane) of the A operand of P V, in place of its S columns
+        // (split mode: the lo plane takes the other 16 columns of the thread's 32)
         tmem_st16(s_tmem0 + 64 * SB(g) + 32 * half + lane_addr, w);
+        if (NSPLIT == 3) tmem_st16(s_tmem0 + 64 * SB(g) + 32 * half + 16 + lane_addr, wl);
         l_part = l_part * corr + rs;
         m_run = m_new;
         // rescale this thread's 32 output dims only when some row of the warp moved its maximum
@@ -496,30 +529,42 @@ bool g_attr_dev[64];       // cudaFuncSetAttribute is per device: one handle per
 }  // namespace
 
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
-                         cudaStream_t s, int fp16) {
+                         cudaStream_t s, int fp16, const __nv_bfloat16* qkv_lo) {
   STK_CHECK(qkv16 && B > 0 && S > 0 && H > 0, -1, "attention_tc5: bad arguments");
   STK_CHECK(out.ld % 8 == 0, -1, "attention_tc5: output pitch must be a multiple of 8");
   STK_CHECK(ctx_keys <= S && ctx_rows <= S && ctx_keys >= 0 && ctx_rows >= 0, -1, "attention_tc5: context limits exceed the sequence");
+  STK_CHECK(!(fp16 && qkv_lo), -1, "attention_tc5: the split mode uses bf16 planes");
   STK_TRY(gemm_tc_init());
   int dev = 0;
   STK_CUDA(cudaGetDevice(&dev));
   STK_CHECK(dev >= 0 && dev < 64, -1, "attention_tc5: device ordinal out of range");
   if (!g_attr_dev[dev]) {
     STK_CUDA(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
-    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A5<1>::SMEM_BYTES));
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, A5<1>::SMEM_BYTES));
+    STK_CUDA(cudaFuncSetAttribute(attention_tc5_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, A5<3>::SMEM_BYTES));
     g_attr_dev[dev] = true;
   }
   const int g_num_sms = g_num_sms_dev[dev];
-  CUtensorMap mq, mkv;
+  CUtensorMap mq, mkv, mql, mkvl;
   const uint64_t rows = (uint64_t)B * S, cols = (uint64_t)3 * H * HD;
   STK_TRY(make_tensor_map_2d(&mq, qkv16, rows, cols, BQ, HD, fp16));
   STK_TRY(make_tensor_map_2d(&mkv, qkv16, rows, cols, BKV, HD, fp16));
+  mql = mq; mkvl = mkv;
+  if (qkv_lo) {
+    STK_TRY(make_tensor_map_2d(&mql, qkv_lo, rows, cols, BQ, HD, 0));
+    STK_TRY(make_tensor_map_2d(&mkvl, qkv_lo, rows, cols, BKV, HD, 0));
+  }
   Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
   const int n_items = ((S + BQ - 1) / BQ) * H * B;
-  dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
-  if (fp16) attention_tc5_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
-  else attention_tc5_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(mq, mkv, p);
+  if (qkv_lo) {
+    dim3 grid(std::min(n_items, g_num_sms));                         // split mode: one (160 KiB) CTA per SM
+    attention_tc5_kernel<false, 3><<<grid, NUM_THREADS, A5<3>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
+  } else {
+    dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
+    if (fp16) attention_tc5_kernel<true, 1><<<grid, NUM_THREADS, A5<1>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
+    else attention_tc5_kernel<false, 1><<<grid, NUM_THREADS, A5<1>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
+  }
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

@@ -3,7 +3,7 @@
 // Host-side orchestration of the encode / decode hot path of mimogpt/infer/SelftokPipeline.py — weights under the
 // reference's checkpoint key names, every input-independent table built once at finalize, one workspace per batch
 // size, and the 50-step sampler captured in one CUDA graph.  All arithmetic is in the kernels of kernels_simt.cu
-// (fp32 FFMA: encoder, VQ, tables), gemm_tc.cu (tcgen05 GEMMs of the MMDiT) and attn_tc.cu (joint attention).
+// (fp32 FFMA: encoder, VQ, tables), gemm_tc.cu (tcgen05 GEMMs of the MMDiT) and attn_tc5.cu (tcgen05 joint attention).
 #include "../../include/selftok_b200.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -60,7 +60,6 @@ struct selftok_engine {
   int D = 0, H = 0, Nimg = 0, Nenc = 0;
   bool finalized = false;
   bool use_graph = true;
-  bool attn_tcgen05 = true;             // single-pass modes: tcgen05/TMEM attention (SELFTOK_ATTN=mma selects the mma.sync kernel)
   std::unordered_map<std::string, Tensor> w;
   std::unordered_map<std::string, WPack> wp;
   std::vector<void*> allocs;            // tables + packed weights
@@ -217,10 +216,6 @@ extern "C" __attribute__((visibility("default"))) int selftok_create(const selft
   e->H = cfg->dit_depth;
   e->Nimg = (cfg->latent / cfg->dit_patch) * (cfg->latent / cfg->dit_patch);
   e->Nenc = (cfg->latent / cfg->enc_patch) * (cfg->latent / cfg->enc_patch);
-  {
-    const char* v = getenv("SELFTOK_ATTN");
-    if (v && std::string(v) == "mma") e->attn_tcgen05 = false;
-  }
   if (tc_mode(e)) {
     int st = gemm_tc_init();
     if (st != 0) { delete e; return st; }
@@ -708,10 +703,7 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
       ao.fp16 = fp16;
       const int ctx_rows = ctx_self ? Kc : 0, ctx_keys = ctx_self ? Kc : 0;
-      if (nsplit(e) == 1 && e->attn_tcgen05)
-        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16));
-      else
-        PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, fp16));
+      PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, fp16, nsplit(e) == 3 ? w.qkv_lo : nullptr));
       // post_attention (mmdit.py:485-496); the pre_only context block of the last layer stops here
       Epilogue erx, erc;
       erx.mode = EPI_RESID; erx.out = w.x; erx.resid = w.x; erx.ldo = D; erx.gate = xmod + 2 * D; erx.gate_ld = 6 * D; erx.gate_period = 1;
@@ -755,10 +747,7 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
     } else {
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
       ao.fp16 = is_fp16(e);
-      if (nsplit(e) == 1 && e->attn_tcgen05)
-        PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e)));
-      else
-        PROF(PC_ATTN, launch_attention_tc(w.qkv_hi, w.qkv_lo, B, S, e->H, nsplit(e), ctx_rows, ctx_keys, ao, s, is_fp16(e)));
+      PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e), nsplit(e) == 3 ? w.qkv_lo : nullptr));
     }
     if (!last)
       STK_TRY(post_attention(e, pc, w.ctx, Mc, cmod, 6 * D, Kc, w.attn_c, w.attn_c_hi, w.attn_c_lo, w.a_c, w.a_c_hi, w.a_c_lo,
@@ -1028,10 +1017,8 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_f32(co
 
 extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(const float* qkv, float* out, int B, int S, int H, int ns, int ctx_rows, int ctx_keys,
                                       void* stream) {
-  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3 || ns == 10 || ns == 11), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
-  const bool tc5 = ns >= 10;                    // 10: tcgen05 kernel, IEEE half; 11: tcgen05 kernel, bf16
-  const int fp16 = ns == 0 || ns == 10;
-  if (ns != 3) ns = 1;
+  STK_CHECK(qkv && out && (ns == 0 || ns == 1 || ns == 3), SELFTOK_ERR_BAD_ARG, "selftok_k_attention_tc: bad argument");
+  const int fp16 = ns == 0;                     // 0: IEEE half, 1: bf16, 3: split bf16 (hi + lo planes, three MMAs per product)
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t n = (int64_t)B * S * 3 * H * 64;
   bf16 *qh, *ql = nullptr;
@@ -1040,8 +1027,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_k_attention_tc(con
   int st = launch_split_bf16(qkv, qh, ql, n, s, fp16);
   AttnOut ao;
   ao.f32_a = out; ao.split = S; ao.ld = (int64_t)H * 64;
-  if (!st && tc5) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16);
-  else if (!st) st = launch_attention_tc(qh, ql, B, S, H, ns, ctx_rows, ctx_keys, ao, s, fp16);
+  if (!st) st = launch_attention_tc5(qh, B, S, H, ctx_rows, ctx_keys, ao, s, fp16, ql);
   cudaStreamSynchronize(s);
   cudaFree(qh);
   if (ql) cudaFree(ql);

@@ -105,13 +105,11 @@ int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream
 int gemm_tc_init();   // resolves cuTensorMapEncodeTiled, sets smem attributes; idempotent
 void gemm_tc_set_ctas(int n);   // 2 (default): cta_group::2 pair kernel; 1: single-CTA kernel
 
-// ---- tensor-core attention (attn_tc.cu) ------------------------------------------------------------------------
-// qkv planes: packed 16-bit [B,S,3,H,64] (hi, and lo for nsplit == 3), written by the QKV GEMM epilogue
-int launch_attention_tc(const __nv_bfloat16* qkv_hi, const __nv_bfloat16* qkv_lo, int B, int S, int H, int nsplit,
-                        int ctx_rows, int ctx_keys, const AttnOut& out, cudaStream_t s, int fp16 = 0);
-
-// tcgen05 / TMEM attention (attn_tc5.cu), single-pass 16-bit operands (fp16 != 0: IEEE half, else bf16)
+// ---- tensor-core attention -----------------------------------------------------------------------------------
+// qkv planes: packed 16-bit [B,S,3,H,64] (hi, and lo for the split mode), written by the QKV GEMM epilogue
+// tcgen05 / TMEM attention (attn_tc5.cu): single-pass 16-bit operands (fp16 != 0: IEEE half, else bf16), or -- with the lo
+// planes given -- the fp32-faithful split-bf16 mode (three MMAs per product, P split in registers)
 int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ctx_rows, int ctx_keys, const AttnOut& out,
-                         cudaStream_t s, int fp16);
+                         cudaStream_t s, int fp16, const __nv_bfloat16* qkv_lo = nullptr);
 
 }  // namespace stk

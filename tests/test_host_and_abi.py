@@ -38,8 +38,10 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
     if not os.path.exists(cuobjdump):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([cuobjdump, "-sass", capi._LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+    for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
+    # no legacy tensor path left: every tensor-core product of the library is a tcgen05.mma (HMMA = mma.sync / wmma)
+    assert not re.search(r"\bHMMA", sass), "legacy mma.sync instructions found in the library"
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

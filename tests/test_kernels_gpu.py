@@ -85,7 +85,7 @@ def test_gemm_tcgen05(dev, M, N, K, nsplit, ctas):
 @pytest.mark.parametrize("B,S,H,ctx_rows,ctx_keys", [(2, 768, 3, 0, 0), (2, 276, 24, 0, 0), (3, 48, 3, 0, 0), (2, 300, 2, 44, 44),
                                                     (1, 768, 4, 512, 512), (2, 65, 1, 0, 0), (2, 1280, 2, 1024, 1024),
                                                     (3, 640, 5, 384, 384), (2, 700, 3, 300, 300), (5, 129, 2, 0, 0)])
-@pytest.mark.parametrize("nsplit", [3, 1, 0, 10, 11])
+@pytest.mark.parametrize("nsplit", [3, 1, 0])
 def test_attention_tensor_core(dev, B, S, H, ctx_rows, ctx_keys, nsplit):
     from selftoktokenizer_b200 import capi
     qkv = _rand((B, S, 3, H, 64), 15, dev)
@@ -97,4 +97,5 @@ def test_attention_tensor_core(dev, B, S, H, ctx_rows, ctx_keys, nsplit):
         mask[:ctx_rows, ctx_keys:] = False
     ref = F.scaled_dot_product_attention(q, k, v, attn_mask=mask).transpose(1, 2).reshape(B, S, H * 64)
     err = (o.double() - ref).abs().max().item()
-    assert err < {3: 3e-5, 1: 2e-2, 0: 3e-3, 10: 3e-3, 11: 2e-2}[nsplit], err      # 10 / 11: tcgen05 + TMEM kernel (fp16 / bf16)
+    # tcgen05 + TMEM kernel: 3 = split bf16 (fp32-faithful), 1 = bf16, 0 = IEEE half
+    assert err < {3: 3e-5, 1: 2e-2, 0: 3e-3}[nsplit], err
