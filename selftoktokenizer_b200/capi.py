@@ -216,12 +216,12 @@ class Engine:
             raise SelftokError(f"{what}: expected [B, {want[0]}, {want[1]}, {want[2]}] latents for this engine "
                                f"(image side {8 * d.latent}), got {tuple(x.shape)}")
 
-    def _check_tokens(self, tokens: torch.Tensor, what: str, batch: Optional[int] = None) -> None:
+    def _check_tokens(self, tokens: torch.Tensor, what: str, batch: Optional[int] = None, is_output: bool = False) -> None:
         if tokens.dim() != 2 or tokens.shape[1] != self.dims.K or tokens.shape[0] < 1:
             raise SelftokError(f"{what}: expected [B, {self.dims.K}] token ids, got {tuple(tokens.shape)}")
         if batch is not None and tokens.shape[0] != batch:
             raise SelftokError(f"{what}: {tokens.shape[0]} token rows for a batch of {batch}")
-        if not tokens.is_cuda:
+        if not tokens.is_cuda and not is_output:
             # ids outside the codebook are an error in the reference (`codebook[idx]` raises).  Host tensors are checked here
             # for free; device tensors are checked by the kernel (NaN rows + counter, see `id_errors`).
             lo, hi = int(tokens.min()), int(tokens.max())
@@ -306,7 +306,7 @@ class Engine:
                 or not x0.is_contiguous() or not tokens_out.is_contiguous():
             raise SelftokError("encode_host: contiguous host tensors (fp32 latents, int64 tokens) expected")
         self._check_latent(x0, "encode_host")
-        self._check_tokens(tokens_out, "encode_host", x0.shape[0])
+        self._check_tokens(tokens_out, "encode_host", x0.shape[0], is_output=True)
         with torch.cuda.device(self.device):
             check(self.lib.selftok_encode_host(self.h, x0.data_ptr(), x0.shape[0], tokens_out.data_ptr(), _stream_ptr(self.device)))
         return tokens_out
