@@ -105,6 +105,14 @@ int selftok_set_schedule(selftok_handle_t h, int steps, const float* t_host, con
  * positional embeddings) on the device, and frees staging copies. */
 int selftok_finalize(selftok_handle_t h, void* stream);
 
+/* ---- prepack cache: the finalized device state (fp32 tensors that stay fp32, 16-bit operand planes, static tables,
+ * schedule) as one file.  selftok_export_packed needs a finalized handle; selftok_import_packed needs a FRESH handle
+ * (selftok_create only) of the same configuration / precision and leaves it finalized -- no selftok_load_tensor,
+ * selftok_set_schedule or selftok_finalize.  Replaces the per-process torch.load + load_state_dict of the fp32 checkpoint
+ * (SelftokPipeline.py:188-199). */
+int selftok_export_packed(selftok_handle_t h, const char* path);
+int selftok_import_packed(selftok_handle_t h, const char* path);
+
 /* ---- hot path, device buffers ---------------------------------------------------------------------------- */
 /* x0_dev [B,C,latent,latent] fp32 (VAE latent after SD3LatentFormat.process_in) -> tokens_dev [B,K] int64,
  * outs_q_dev [B,K,code_dim] fp32 (may be NULL), feats_dev [B,K,enc_qdim] fp32 pre-VQ features (may be NULL). */
@@ -120,6 +128,14 @@ int selftok_lookup(selftok_handle_t h, const int64_t* tokens_dev, int B, float* 
  * x0_out_dev may alias noise_dev. */
 int selftok_decode(selftok_handle_t h, const int64_t* tokens_dev, const float* noise_dev, int B, int steps,
                    float* x0_out_dev, void* stream);
+/* Guided sampler (classifier-free guidance): the reference's p_sample_loop(..., uncond_scale = cfg_scale)
+ * (sd3/rectified_flow.py:165-294, 280-289): per step one conditional evaluation (context rows blind to the image keys, as that
+ * call site omits context_see_xt) and MMDiT.cfg_inference (sd3/mmdit.py:1117-1163: no context, integer timestep), combined as
+ * v_u + cfg_scale (v_c - v_u).  selftok_set_cfg_schedule (host pointer, [steps,256] sinusoidal features of
+ * floor(1000 t_i).clamp(0, 999)) must be called between selftok_set_schedule and selftok_finalize. */
+int selftok_set_cfg_schedule(selftok_handle_t h, const float* t_freq_uncond_host);
+int selftok_decode_cfg(selftok_handle_t h, const int64_t* tokens_dev, const float* noise_dev, int B, int steps,
+                       float cfg_scale, float* x0_out_dev, void* stream);
 /* One MMDiT velocity evaluation at schedule index `step` on latents x_dev (testing / bisecting entry). */
 int selftok_dit_velocity(selftok_handle_t h, const int64_t* tokens_dev, const float* x_dev, int B, int step,
                          float* v_out_dev, void* stream);

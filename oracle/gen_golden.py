@@ -231,6 +231,28 @@ def gen_mid(stress=False):
     save("mid_stress" if stress else "mid", tokens=tokens, margin=margin, noise=noise, pred_x0=pred_x0, v0=v0, v49=v49)
 
 
+def gen_tiny_cfg():
+    """The guided sampler of the reference: p_sample_loop(..., uncond_scale = 2.5) on the TINY checkpoint -- the pipeline never
+    forwards cfg_scale (SelftokPipeline.py:266-282), so the loop is called here with the pipeline's own arguments + uncond_scale."""
+    dims = C.TINY
+    pipe, _ = build(dims, tag="tinycfg")
+    g = np.load(os.path.join(GOLD, "tiny.npz"))
+    tokens = torch.from_numpy(g["tokens"])
+    noise = torch.from_numpy(g["noise"])
+    B = tokens.shape[0]
+    outs_q = lookup(pipe, tokens)
+    k = pipe.diti.to_indices(torch.tensor([pipe.flow.timestep_map[0]] * B).long())
+    enc_mask = pipe.model.encoder.get_encoder_mask(tokens, k)
+    ehs = outs_q * enc_mask[..., None].expand_as(outs_q)
+    model_kwargs = dict(encoder_hidden_states=ehs, mask=enc_mask, context_see_xt=True)
+    with torch.no_grad():
+        pred = pipe.flow.p_sample_loop(pipe.model.model, noise.shape, noise.clone(), model_kwargs=model_kwargs, start_t=pipe._steps,
+                                       cond_vary=pipe.cond_vary, diti=pipe.diti, encoder=pipe.model.encoder, x_0=noise.float(),
+                                       ori_hidden_states=outs_q, uncond_scale=2.5)
+    print("cfg 2.5 vs plain sampler: max-abs difference", float((pred - torch.from_numpy(g["pred_x0"])).abs().max()))
+    save("tiny_cfg", pred_x0=pred, cfg_scale=np.float32(2.5))
+
+
 def gen_tiny_renderer():
     dims = TINY_R
     pipe, _ = build(dims, tag="tinyr")
@@ -351,6 +373,8 @@ if __name__ == "__main__":
             gen_full_decode(pipe)
         elif w == "full_renderer":
             gen_full_renderer()
+        elif w == "tiny_cfg":
+            gen_tiny_cfg()
         elif w == "mid":
             gen_mid(False)
         elif w == "mid_stress":

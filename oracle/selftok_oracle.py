@@ -269,6 +269,45 @@ def decode(sd: SD, d: SelftokDims, tokens: torch.Tensor, noise: torch.Tensor, st
     return x
 
 
+def dit_velocity_uncond(sd: SD, d: SelftokDims, x_lat: torch.Tensor, t_freq_u_row: torch.Tensor) -> torch.Tensor:
+    """MMDiT.cfg_inference (sd3/mmdit.py:1117-1163) as sample_one_step calls it (encoder_hidden_states=None, mask = zeros):
+    context = zeros and every context key masked for EVERY row -> restated here without truncation (K zero rows kept)."""
+    B = x_lat.shape[0]
+    D = d.dit_hidden
+    g = d.latent // d.dit_patch
+    w = sd["model.x_embedder.proj.weight"].reshape(D, -1)
+    x = _linear_impl(_patchify(x_lat.float(), d.dit_patch), w, sd["model.x_embedder.proj.bias"])
+    x = x + _center_crop_pos(sd["model.pos_embed"], d.dit_pos_max, g, g)
+    c = _t_embed(sd, "model.t_embedder", t_freq_u_row.reshape(1, -1)).expand(B, -1)       # integer timestep (mmdit.py:1127-1130)
+    ctx = torch.zeros(B, d.K, D)                                                          # mmdit.py:1146 (no pos embed, no embedder)
+    pos_freq = sched.make_tables(d.K, d.stages, d.k_per_stage, 1).pos_freq
+    # mask = cat(zeros, ones) repeated for every row (mmdit.py:1158-1159): all rows, context rows included, see the image keys only
+    out = joint_blocks(sd, d, ctx, x, c, pos_freq, n_vis=0, ctx_sees_x=True, truncate=False)
+    return _unpatchify(out, d)
+
+
+def decode_cfg(sd: SD, d: SelftokDims, tokens: torch.Tensor, noise: torch.Tensor, cfg_scale: float, steps: int = 50) -> torch.Tensor:
+    """p_sample_loop with uncond_scale = cfg_scale (rectified_flow.py:165-256) -> sample_one_step's guided branch (:280-289):
+    out_uncond = cfg_inference(x, t, None, None, mask = 0); out = model(x, t, None, context, mask = ori_mask) -- WITHOUT
+    context_see_xt (default False: context rows only see the visible context keys); v = out_uncond + s (out - out_uncond)."""
+    tb = sched.make_tables(d.K, d.stages, d.k_per_stage, steps)
+    outs_q = lookup(sd, d, tokens)
+    x = noise.float().clone()
+    for i in range(steps):
+        n_vis = int(tb.k[i]) + 1
+        B = x.shape[0]
+        D = d.dit_hidden
+        g = d.latent // d.dit_patch
+        w = sd["model.x_embedder.proj.weight"].reshape(D, -1)
+        xe = _linear_impl(_patchify(x, d.dit_patch), w, sd["model.x_embedder.proj.bias"])
+        xe = xe + _center_crop_pos(sd["model.pos_embed"], d.dit_pos_max, g, g)
+        c = _t_embed(sd, "model.t_embedder", tb.t_freq[i].reshape(1, -1)).expand(B, -1)
+        v_c = _unpatchify(joint_blocks(sd, d, context_embed(sd, outs_q), xe, c, tb.pos_freq, n_vis, ctx_sees_x=False, truncate=False), d)
+        v_u = dit_velocity_uncond(sd, d, x, tb.t_freq_uncond[i])
+        x = x - tb.dt[i] * (v_u + cfg_scale * (v_c - v_u))
+    return x
+
+
 def render(sd: SD, d: SelftokDims, tokens: torch.Tensor, truncate: bool = False) -> torch.Tensor:
     """decoding_with_renderer up to pred_x0 (SelftokPipeline.py:296-310): one MMDiT_Renderer.forward
     (sd3/mmdit.py:1511-1620): x = mask_token + positional_embedding, t = 1000 (no *1000), context rows see context only."""

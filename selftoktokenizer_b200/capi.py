@@ -22,8 +22,8 @@ PREC = {"fp32": 0, "bf16x3": 1, "bf16": 2, "fp16": 3}
 # every symbol include/selftok_b200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
     "selftok_create", "selftok_destroy", "selftok_last_error", "selftok_version", "selftok_load_tensor",
-    "selftok_set_schedule", "selftok_finalize", "selftok_encode", "selftok_vq_argmax", "selftok_lookup",
-    "selftok_decode", "selftok_dit_velocity", "selftok_render", "selftok_encode_host", "selftok_decode_host",
+    "selftok_set_schedule", "selftok_finalize", "selftok_export_packed", "selftok_import_packed", "selftok_encode", "selftok_vq_argmax", "selftok_lookup",
+    "selftok_set_cfg_schedule", "selftok_decode", "selftok_decode_cfg", "selftok_dit_velocity", "selftok_render", "selftok_encode_host", "selftok_decode_host",
     "selftok_render_host", "selftok_id_errors", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
     "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_set_gemm_ctas", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
     "selftok_k_attention_tc",
@@ -62,10 +62,14 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.selftok_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, i32, C.POINTER(i64), i32]
     lib.selftok_set_schedule.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     lib.selftok_finalize.argtypes = [vp, vp]
+    lib.selftok_export_packed.argtypes = [vp, C.c_char_p]
+    lib.selftok_import_packed.argtypes = [vp, C.c_char_p]
     lib.selftok_encode.argtypes = [vp, vp, i32, vp, vp, vp, vp]
     lib.selftok_vq_argmax.argtypes = [vp, vp, i64, vp, vp, vp]
     lib.selftok_lookup.argtypes = [vp, vp, i32, vp, vp]
     lib.selftok_decode.argtypes = [vp, vp, vp, i32, i32, vp, vp]
+    lib.selftok_set_cfg_schedule.argtypes = [vp, vp]
+    lib.selftok_decode_cfg.argtypes = [vp, vp, vp, i32, i32, C.c_float, vp, vp]
     lib.selftok_dit_velocity.argtypes = [vp, vp, vp, i32, i32, vp, vp]
     lib.selftok_render.argtypes = [vp, vp, i32, vp, vp]
     lib.selftok_encode_host.argtypes = [vp, vp, i32, vp, vp]
@@ -109,14 +113,29 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class Engine:
     """One handle (`selftok_handle_t`) on one device: weights, static tables, workspaces, CUDA graphs."""
 
-    def __init__(self, dims: SelftokDims, state_dict: Dict[str, torch.Tensor], device="cuda:0", precision: str = "auto",
-                 steps: int = 50, start: float = 1.0):
+    def __init__(self, dims: SelftokDims, state_dict: Optional[Dict[str, torch.Tensor]], device="cuda:0", precision: str = "auto",
+                 steps: int = 50, start: float = 1.0, pack_path: Optional[str] = None):
+        """`pack_path`: prepack cache file (selftok_export_packed / selftok_import_packed).  If it exists the engine is
+        restored from it and `state_dict` may be None (no torch.load of the fp32 checkpoint at all); otherwise the engine is
+        built from `state_dict` and, when a path is given, exported there.  The precision chosen by 'auto' is kept in a
+        JSON sidecar next to the file."""
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise SelftokError("no CUDA device: selftok_b200 has no CPU fallback")
         self.dims = dims
         self.device = torch.device(device)
         probe = False
+        self.restored_from_pack = False
+        side = pack_path + ".json" if pack_path else None
+        if pack_path and os.path.exists(pack_path) and os.path.exists(side):
+            import json
+            meta = json.load(open(side))
+            if meta.get("requested") == precision and meta.get("steps") == (1 if dims.renderer else steps) and meta.get("start") == start:
+                precision = meta["precision"]
+                self.restored_from_pack = True
+        if state_dict is None and not self.restored_from_pack:
+            raise SelftokError("Engine: no state_dict and no usable prepack cache")
+        requested = precision if not self.restored_from_pack else meta["requested"]
         if precision == "auto":
             # One-pass renderer: its output IS one network evaluation (single-pass fp16 measures 1.05e-3 there), and a pass
             # costs 1/50 of a decode, so it always runs the fp32-faithful split-bf16 arithmetic (5e-5).
@@ -141,7 +160,8 @@ class Engine:
         check(self.lib.selftok_create(C.byref(cfg), C.byref(h)))
         self.h = h
         try:
-            self._load(state_dict)
+            if not self.restored_from_pack:
+                self._load(state_dict)
             if dims.renderer:
                 # MMDiT_Renderer: one pass at t = 1000 with all K tokens visible (sd3/mmdit.py:1523)
                 tb = sched.make_tables(dims.K, dims.stages, dims.k_per_stage, 1)
@@ -158,12 +178,26 @@ class Engine:
             dt = np.ascontiguousarray(tb.dt.numpy(), dtype=np.float32)
             tf = np.ascontiguousarray(t_freq.numpy(), dtype=np.float32)
             pf = np.ascontiguousarray(tb.pos_freq.numpy(), dtype=np.float32)
-            check(self.lib.selftok_set_schedule(self.h, self.steps, t.ctypes.data, dt.ctypes.data, k.ctypes.data,
-                                                tf.ctypes.data, pf.ctypes.data))
-            with torch.cuda.device(self.device):
-                check(self.lib.selftok_finalize(self.h, _stream_ptr(self.device)))
-            if probe:
-                self._auto_probe(state_dict, steps, start)
+            if self.restored_from_pack:
+                with torch.cuda.device(self.device):
+                    check(self.lib.selftok_import_packed(self.h, pack_path.encode()))
+                self.auto_probe = meta.get("auto_probe")
+            else:
+                check(self.lib.selftok_set_schedule(self.h, self.steps, t.ctypes.data, dt.ctypes.data, k.ctypes.data,
+                                                    tf.ctypes.data, pf.ctypes.data))
+                if not dims.renderer:                       # tables of the guided sampler's unconditional branch (44 MB)
+                    tu = np.ascontiguousarray(tb.t_freq_uncond.numpy(), dtype=np.float32)
+                    check(self.lib.selftok_set_cfg_schedule(self.h, tu.ctypes.data))
+                with torch.cuda.device(self.device):
+                    check(self.lib.selftok_finalize(self.h, _stream_ptr(self.device)))
+                if probe:
+                    self._auto_probe(state_dict, steps, start)
+                if pack_path:
+                    import json
+                    with torch.cuda.device(self.device):
+                        check(self.lib.selftok_export_packed(self.h, pack_path.encode()))
+                    json.dump({"requested": requested, "precision": self.precision, "steps": self.steps, "start": start,
+                               "auto_probe": self.auto_probe}, open(side, "w"))
         except Exception:
             self.close()
             raise
@@ -278,6 +312,18 @@ class Engine:
         with torch.cuda.device(self.device):
             check(self.lib.selftok_decode(self.h, tokens.data_ptr(), noise.data_ptr(), B, steps or self.steps,
                                           out.data_ptr(), _stream_ptr(self.device)))
+        return out
+
+    def decode_cfg(self, tokens: torch.Tensor, noise: torch.Tensor, cfg_scale: float, steps: Optional[int] = None) -> torch.Tensor:
+        """Guided sampler: the reference's p_sample_loop(..., uncond_scale=cfg_scale) (rectified_flow.py:280-289)."""
+        self._check_latent(noise, "decode_cfg (noise)")
+        self._check_tokens(tokens, "decode_cfg", noise.shape[0])
+        tokens = self._dev(tokens, torch.int64)
+        noise = self._dev(noise, torch.float32)
+        out = torch.empty_like(noise)
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_decode_cfg(self.h, tokens.data_ptr(), noise.data_ptr(), tokens.shape[0], steps or self.steps,
+                                              float(cfg_scale), out.data_ptr(), _stream_ptr(self.device)))
         return out
 
     def dit_velocity(self, tokens: torch.Tensor, x: torch.Tensor, step: int) -> torch.Tensor:

@@ -8,7 +8,9 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <map>
 #include <string>
 #include <unordered_map>
@@ -38,6 +40,7 @@ struct DecodeWs {       // activation workspace of the MMDiT for one batch size
   int64_t* tokens = nullptr;
   float *outs_q = nullptr, *x_lat = nullptr, *patch = nullptr, *ctx0 = nullptr, *ctx = nullptr, *x = nullptr;
   float *qkv = nullptr, *o_final = nullptr;      // qkv: fp32 joint buffer (fp32 mode only)
+  float* o_final_u = nullptr;                    // final-layer output of the unconditional branch (guided sampler)
   bf16 *qkv_hi = nullptr, *qkv_lo = nullptr;     // joint q/k/v as 16-bit planes [B,S,3,H,64] (tensor-core modes)
   // fp32 mode activations
   float *a_c = nullptr, *a_x = nullptr, *attn_c = nullptr, *attn_x = nullptr, *h_c = nullptr, *h_x = nullptr;
@@ -69,10 +72,13 @@ struct selftok_engine {
   std::vector<float> t, dt;
   std::vector<int> k;
   float *t_freq = nullptr, *pos_freq = nullptr;
+  float* t_freq_u = nullptr;            // classifier-free guidance: features of floor(1000 t).clamp(0, 999) (MMDiT.cfg_inference)
   // tables
   float *enc_mod = nullptr, *enc_pos = nullptr, *cbt = nullptr;
   float *ctx_mod = nullptr, *x_mod = nullptr, *ctx_last_mod = nullptr, *final_mod = nullptr, *dit_pos = nullptr;
+  float *x_mod_u = nullptr, *final_mod_u = nullptr;     // unconditional branch of the guided sampler (optional)
   float* rend_x0 = nullptr;
+  bool has_cfg = false;                 // unconditional-branch tables built (selftok_set_cfg_schedule before finalize)
   int* bad_ids = nullptr;               // device counter of out-of-range token ids seen by the lookup kernel
   DecodeWs dws;
   EncodeWs ews;
@@ -284,6 +290,18 @@ extern "C" __attribute__((visibility("default"))) int selftok_set_schedule(selft
   return SELFTOK_OK;
 }
 
+// Optional, before finalize: sinusoidal features [steps,256] of floor(1000 t_i).clamp(0, 999), the timestep the unconditional
+// branch of the guided sampler is embedded with (MMDiT.cfg_inference, sd3/mmdit.py:1127).  Enables selftok_decode_cfg.
+extern "C" __attribute__((visibility("default"))) int selftok_set_cfg_schedule(selftok_handle_t e, const float* t_freq_uncond_host) {
+  STK_CHECK(e && t_freq_uncond_host, SELFTOK_ERR_BAD_ARG, "selftok_set_cfg_schedule: bad argument");
+  STK_CHECK(!e->finalized && e->steps > 0, SELFTOK_ERR_STATE, "selftok_set_cfg_schedule: after selftok_set_schedule, before selftok_finalize");
+  STK_CHECK(!e->cfg.renderer, SELFTOK_ERR_STATE, "the renderer has no guided path");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  if (!e->t_freq_u) STK_TRY(dalloc(e, e->allocs, &e->t_freq_u, (int64_t)e->steps * 256));
+  STK_CUDA(cudaMemcpy(e->t_freq_u, t_freq_uncond_host, sizeof(float) * e->steps * 256, cudaMemcpyHostToDevice));
+  return SELFTOK_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ finalize
 // adaLN table of a position-indexed block:  Linear(SiLU(t_embedder(pos_freq)))  (modules.py:311-318; mmdit.py:446-458)
 static int build_pos_table(selftok_engine* e, const std::string& blk, const float* freq, int rows, float* tmp1, float* tmp2,
@@ -359,6 +377,24 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
     Epilogue e4;
     e4.out = e->final_mod;
     STK_TRY(lin32(e, "model.final_layer.adaLN_modulation.1", csil, D, T, e4, s));
+    if (e->t_freq_u) {
+      // unconditional branch of the guided sampler: same MLPs on the integer-floored timestep (mmdit.py:1127-1130), image
+      // stream only (every row of that pass is blind to the context keys, so the context stream never reaches the output)
+      ep.act = ACT_SILU; ep.out = tmp1;
+      STK_TRY(lin32(e, "model.t_embedder.mlp.0", e->t_freq_u, 256, T, ep, s));
+      ep.out = csil;
+      STK_TRY(lin32(e, "model.t_embedder.mlp.2", tmp1, D, T, ep, s));
+      STK_TRY(dalloc(e, e->allocs, &e->x_mod_u, (int64_t)L * T * 6 * D));
+      for (int j = 0; j < L; ++j) {
+        Epilogue e2;
+        e2.out = e->x_mod_u + (int64_t)j * T * 6 * D;
+        STK_TRY(lin32(e, "model.joint_blocks." + std::to_string(j) + ".x_block.adaLN_modulation.1", csil, D, T, e2, s));
+      }
+      STK_TRY(dalloc(e, e->allocs, &e->final_mod_u, (int64_t)T * 2 * D));
+      Epilogue e5;
+      e5.out = e->final_mod_u;
+      STK_TRY(lin32(e, "model.final_layer.adaLN_modulation.1", csil, D, T, e5, s));
+    }
   }
   if (c.renderer) {
     GETW(pe, "model.positional_embedding");
@@ -404,6 +440,172 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
     cudaFree(t.d);
     t.d = nullptr;
     e->bytes -= t.numel * 4;
+  }
+  e->has_cfg = e->x_mod_u != nullptr;
+  e->finalized = true;
+  return SELFTOK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ prepack cache
+// The finalized device state (fp32 tensors that stay fp32, 16-bit operand planes, every static table, the schedule) as ONE
+// file, so that a later process skips torch.load of the fp32 checkpoint, the per-tensor uploads, the table MLPs and the
+// packing (checkpoint loader + prepack cache; SelftokPipeline.py:188-199 reloads 8.3 GB of fp32 per process).
+struct TableRef { const char* tag; float** ptr; int64_t numel; };
+static std::vector<TableRef> table_refs(selftok_engine* e) {
+  const selftok_config_t& c = e->cfg;
+  const int64_t K = c.K, Q = c.enc_qdim, D = e->D, L = c.dit_depth, T = e->steps;
+  const int64_t ge = c.latent / c.enc_patch, gd = c.latent / c.dit_patch;
+  std::vector<TableRef> t = {
+      {"t_freq", &e->t_freq, T * 256}, {"pos_freq", &e->pos_freq, K * 256},
+      {"enc_mod", &e->enc_mod, (int64_t)c.enc_depth * K * 6 * Q}, {"enc_pos", &e->enc_pos, ge * ge * c.enc_hidden},
+      {"cbt", &e->cbt, (int64_t)c.codebook_size * c.code_dim},
+      {"ctx_mod", &e->ctx_mod, (L - 1 > 0 ? L - 1 : 1) * K * 6 * D}, {"x_mod", &e->x_mod, L * T * 6 * D},
+      {"ctx_last_mod", &e->ctx_last_mod, T * 2 * D}, {"final_mod", &e->final_mod, T * 2 * D}};
+  if (c.renderer) t.push_back({"rend_x0", &e->rend_x0, (int64_t)e->Nimg * D});
+  else t.push_back({"dit_pos", &e->dit_pos, gd * gd * D});
+  if (e->has_cfg) {
+    t.push_back({"x_mod_u", &e->x_mod_u, L * T * 6 * D});
+    t.push_back({"final_mod_u", &e->final_mod_u, T * 2 * D});
+  }
+  return t;
+}
+static const char kPackMagic[8] = {'S', 'T', 'K', 'P', 'A', 'C', 'K', '3'};
+static bool same_model(const selftok_config_t& a, const selftok_config_t& b) {
+  selftok_config_t x = a, y = b;
+  x.device = y.device = 0;
+  return memcmp(&x, &y, sizeof(x)) == 0;
+}
+namespace {
+struct PackIO {
+  FILE* f = nullptr;
+  void* bounce = nullptr;                                     // pinned staging buffer
+  static constexpr size_t CH = 64u << 20;
+  ~PackIO() { if (f) fclose(f); if (bounce) cudaFreeHost(bounce); }
+  bool w(const void* p, size_t n) { return fwrite(p, 1, n, f) == n; }
+  bool r(void* p, size_t n) { return fread(p, 1, n, f) == n; }
+  bool wdev(const void* d, size_t n) {
+    for (size_t o = 0; o < n; o += CH) {
+      const size_t m = n - o < CH ? n - o : CH;
+      if (cudaMemcpy(bounce, (const char*)d + o, m, cudaMemcpyDeviceToHost) != cudaSuccess || !w(bounce, m)) return false;
+    }
+    return true;
+  }
+  bool rdev(void* d, size_t n) {
+    for (size_t o = 0; o < n; o += CH) {
+      const size_t m = n - o < CH ? n - o : CH;
+      if (!r(bounce, m) || cudaMemcpy((char*)d + o, bounce, m, cudaMemcpyHostToDevice) != cudaSuccess) return false;
+    }
+    return true;
+  }
+  bool wstr(const std::string& s) { uint32_t n = (uint32_t)s.size(); return w(&n, 4) && w(s.data(), n); }
+  bool rstr(std::string& s) { uint32_t n = 0; if (!r(&n, 4) || n > 4096) return false; s.resize(n); return r(&s[0], n); }
+};
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int selftok_export_packed(selftok_handle_t e, const char* path) {
+  STK_CHECK(e && path, SELFTOK_ERR_BAD_ARG, "selftok_export_packed: bad argument");
+  STK_CHECK(e->finalized, SELFTOK_ERR_STATE, "selftok_export_packed: finalize first");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  STK_CUDA(cudaDeviceSynchronize());
+  PackIO io;
+  const std::string tmp = std::string(path) + ".tmp";
+  io.f = fopen(tmp.c_str(), "wb");
+  STK_CHECK(io.f, SELFTOK_ERR_BAD_ARG, "selftok_export_packed: cannot open the file for writing");
+  STK_CUDA(cudaMallocHost(&io.bounce, PackIO::CH));
+  bool ok = io.w(kPackMagic, 8);
+  const uint32_t cfg_bytes = sizeof(selftok_config_t), steps = (uint32_t)e->steps, has_cfg = e->has_cfg ? 1u : 0u;
+  ok = ok && io.w(&cfg_bytes, 4) && io.w(&e->cfg, cfg_bytes) && io.w(&has_cfg, 4) && io.w(&steps, 4) && io.w(e->t.data(), 4 * steps) &&
+       io.w(e->dt.data(), 4 * steps) && io.w(e->k.data(), 4 * steps);
+  const uint32_t n_w = (uint32_t)e->w.size(), n_p = (uint32_t)e->wp.size();
+  ok = ok && io.w(&n_w, 4);
+  for (auto& kv : e->w) {
+    if (!ok) break;
+    const Tensor& t = kv.second;
+    const uint32_t nd = (uint32_t)t.shape.size(), has = t.d != nullptr;
+    ok = io.wstr(kv.first) && io.w(&nd, 4) && io.w(t.shape.data(), 8 * nd) && io.w(&has, 4);
+    if (ok && has) ok = io.wdev(t.d, sizeof(float) * (size_t)t.numel);
+  }
+  ok = ok && io.w(&n_p, 4);
+  for (auto& kv : e->wp) {
+    if (!ok) break;
+    const int64_t numel = e->w[kv.first].numel;
+    const uint32_t has_lo = kv.second.lo != nullptr;
+    ok = io.wstr(kv.first) && io.w(&numel, 8) && io.w(&has_lo, 4) && io.wdev(kv.second.hi, 2 * (size_t)numel);
+    if (ok && has_lo) ok = io.wdev(kv.second.lo, 2 * (size_t)numel);
+  }
+  for (const TableRef& t : table_refs(e)) {
+    if (!ok) break;
+    ok = io.wstr(t.tag) && io.w(&t.numel, 8) && io.wdev(*t.ptr, sizeof(float) * (size_t)t.numel);
+  }
+  fclose(io.f);
+  io.f = nullptr;
+  if (!ok) { remove(tmp.c_str()); set_error("selftok_export_packed: write failed"); return SELFTOK_ERR_CUDA; }
+  STK_CHECK(rename(tmp.c_str(), path) == 0, SELFTOK_ERR_BAD_ARG, "selftok_export_packed: rename failed");
+  return SELFTOK_OK;
+}
+
+// Fresh handle (selftok_create only) -> the finalized state of the file.  The file must have been exported for the same
+// model configuration, precision and schedule length; anything else is SELFTOK_ERR_BAD_ARG and the handle stays fresh.
+extern "C" __attribute__((visibility("default"))) int selftok_import_packed(selftok_handle_t e, const char* path) {
+  STK_CHECK(e && path, SELFTOK_ERR_BAD_ARG, "selftok_import_packed: bad argument");
+  STK_CHECK(!e->finalized && e->w.empty() && e->steps == 0, SELFTOK_ERR_STATE, "selftok_import_packed: the handle is not fresh");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  PackIO io;
+  io.f = fopen(path, "rb");
+  STK_CHECK(io.f, SELFTOK_ERR_BAD_ARG, "selftok_import_packed: cannot open the file");
+  char magic[8];
+  uint32_t cfg_bytes = 0, steps = 0;
+  selftok_config_t fc;
+  STK_CHECK(io.r(magic, 8) && memcmp(magic, kPackMagic, 8) == 0 && io.r(&cfg_bytes, 4) && cfg_bytes == sizeof(fc) && io.r(&fc, cfg_bytes),
+            SELFTOK_ERR_BAD_ARG, "selftok_import_packed: not a selftok_b200 pack file of this ABI");
+  STK_CHECK(same_model(fc, e->cfg), SELFTOK_ERR_BAD_ARG, "selftok_import_packed: the file was exported for another configuration / precision");
+  uint32_t has_cfg = 0;
+  STK_CHECK(io.r(&has_cfg, 4) && io.r(&steps, 4) && steps > 0 && steps < 100000, SELFTOK_ERR_BAD_ARG, "selftok_import_packed: bad header");
+  e->has_cfg = has_cfg != 0;
+  STK_CUDA(cudaMallocHost(&io.bounce, PackIO::CH));
+  e->steps = (int)steps;
+  e->t.resize(steps); e->dt.resize(steps); e->k.resize(steps);
+  bool ok = io.r(e->t.data(), 4 * steps) && io.r(e->dt.data(), 4 * steps) && io.r(e->k.data(), 4 * steps);
+  uint32_t n_w = 0, n_p = 0;
+  ok = ok && io.r(&n_w, 4) && n_w < 100000;
+  for (uint32_t i = 0; ok && i < n_w; ++i) {
+    std::string name;
+    uint32_t nd = 0, has = 0;
+    Tensor t;
+    ok = io.rstr(name) && io.r(&nd, 4) && nd <= 8;
+    if (!ok) break;
+    t.shape.resize(nd);
+    ok = io.r(t.shape.data(), 8 * nd) && io.r(&has, 4);
+    t.numel = 1;
+    for (int64_t d : t.shape) t.numel *= d;
+    if (ok && has) {
+      ok = cudaMalloc(&t.d, sizeof(float) * (size_t)t.numel) == cudaSuccess && io.rdev(t.d, sizeof(float) * (size_t)t.numel);
+      e->bytes += t.numel * 4;
+    }
+    e->w[name] = t;
+  }
+  ok = ok && io.r(&n_p, 4) && n_p < 100000;
+  for (uint32_t i = 0; ok && i < n_p; ++i) {
+    std::string name;
+    int64_t numel = 0;
+    uint32_t has_lo = 0;
+    WPack pk;
+    ok = io.rstr(name) && io.r(&numel, 8) && io.r(&has_lo, 4) && numel > 0;
+    if (!ok) break;
+    ok = dalloc(e, e->allocs, &pk.hi, numel) == 0 && io.rdev(pk.hi, 2 * (size_t)numel);
+    if (ok && has_lo) ok = dalloc(e, e->allocs, &pk.lo, numel) == 0 && io.rdev(pk.lo, 2 * (size_t)numel);
+    e->wp[name] = pk;
+  }
+  for (const TableRef& t : table_refs(e)) {
+    if (!ok) break;
+    std::string tag;
+    int64_t numel = 0;
+    ok = io.rstr(tag) && tag == t.tag && io.r(&numel, 8) && numel == t.numel && dalloc(e, e->allocs, t.ptr, numel) == 0 &&
+         io.rdev(*t.ptr, sizeof(float) * (size_t)numel);
+  }
+  if (!ok) {
+    set_error("selftok_import_packed: truncated or mismatching pack file (destroy the handle)");
+    return SELFTOK_ERR_BAD_ARG;
   }
   e->finalized = true;
   return SELFTOK_OK;
@@ -589,6 +791,7 @@ static int ensure_dws(selftok_engine* e, int B) {
   STK_TRY(dalloc(e, P, &w.ctx, B * K * D));
   STK_TRY(dalloc(e, P, &w.x, B * N * D));
   STK_TRY(dalloc(e, P, &w.o_final, B * N * c.dit_patch * c.dit_patch * c.in_channels));
+  STK_TRY(dalloc(e, P, &w.o_final_u, B * N * c.dit_patch * c.dit_patch * c.in_channels));
   STK_TRY(dalloc(e, P, &w.a_x, B * N * D));                       // fp32 LN output of the final layer (both modes)
   if (!tc_mode(e)) {
     STK_TRY(dalloc(e, P, &w.qkv, B * S * 3 * D));
@@ -667,17 +870,25 @@ static int post_attention(selftok_engine* e, const std::string& blk, float* resi
 //   Kc         visible context rows (prefix; rows >= Kc are dropped — exact, SURVEY 8a note)
 //   step       row of the per-step tables (x adaLN, final adaLN, last-layer context adaLN)
 //   ctx_self   context rows attend to context keys only (renderer; mmdit.py:1581)
-static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_self, cudaStream_t s) {
+//   uncond     unconditional branch of the guided sampler (MMDiT.cfg_inference, mmdit.py:1117-1163): Kc must be 0 (no row of
+//              that pass sees a context key, so the context stream is dropped -- exact), x-stream adaLN from the integer timestep
+//   o_out      final-layer output [B*N, p*p*C]
+static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_self, cudaStream_t s, bool uncond = false,
+                        float* o_out = nullptr) {
   const selftok_config_t& c = e->cfg;
   DecodeWs& w = e->dws;
   const int D = e->D, N = e->Nimg, L = c.dit_depth, T = e->steps, S = Kc + N;
   const int64_t Mc = (int64_t)B * Kc, Mx = (int64_t)B * N;
+  const bool ctx = Kc > 0;                                                      // is there a context stream in this pass at all
+  STK_CHECK(!uncond || (!ctx && e->x_mod_u), SELFTOK_ERR_STATE, "unconditional pass needs the guided-sampler tables and no context");
+  const float* x_mod_base = uncond ? e->x_mod_u : e->x_mod;
   for (int j = 0; j < L; ++j) {
     const bool last = j == L - 1;
+    const bool ctx_post = ctx && !last;                                         // the last context block is pre_only
     const std::string pc = "model.joint_blocks." + std::to_string(j) + ".context_block.";
     const std::string px = "model.joint_blocks." + std::to_string(j) + ".x_block.";
     const float* cmod = e->ctx_mod + (int64_t)j * c.K * 6 * D;                  // [K][6D]
-    const float* xmod = e->x_mod + ((int64_t)j * T + step) * 6 * D;             // [6D]
+    const float* xmod = x_mod_base + ((int64_t)j * T + step) * 6 * D;           // [6D]
     if (tc_mode(e)) {
       // ---- tensor-core path: the two streams' GEMMs of every stage share one launch (lintc2)
       const int fp16 = is_fp16(e);
@@ -689,15 +900,17 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       else { lp[0].shift = lm; lp[0].scale = lm + D; lp[0].ld_mod = 2 * D; lp[0].period = 1; }
       lp[1].x = w.x; lp[1].out_hi = w.a_x_hi; lp[1].out_lo = w.a_x_lo; lp[1].M = Mx;
       lp[1].shift = xmod; lp[1].scale = xmod + D; lp[1].ld_mod = 6 * D; lp[1].period = 1;
-      PROF(PC_LN, launch_ln_mod_pair(lp, 2, D, 1e-6f, s, fp16));
+      if (ctx) PROF(PC_LN, launch_ln_mod_pair(lp, 2, D, 1e-6f, s, fp16));
+      else PROF(PC_LN, launch_ln_mod_pair(lp + 1, 1, D, 1e-6f, s, fp16));
       TcProblem pr[2];
       Epilogue eq;                                                              // q/k/v leave the GEMM as 16-bit planes in the joint buffer
       eq.mode = EPI_SPLIT; eq.out_hi = w.qkv_hi; eq.out_lo = w.qkv_lo; eq.ldo = 3 * D; eq.rpb_out = S;
+      int np = 0;
       eq.rpb_in = Kc; eq.row_off = 0;
-      STK_TRY(tc_problem(e, pc + "attn.qkv", w.a_c_hi, w.a_c_lo, Mc, eq, &pr[0]));
+      if (ctx) STK_TRY(tc_problem(e, pc + "attn.qkv", w.a_c_hi, w.a_c_lo, Mc, eq, &pr[np++]));
       eq.rpb_in = N; eq.row_off = Kc;
-      STK_TRY(tc_problem(e, px + "attn.qkv", w.a_x_hi, w.a_x_lo, Mx, eq, &pr[1]));
-      STK_TRY(lintc2(e, pr, 2, s));
+      STK_TRY(tc_problem(e, px + "attn.qkv", w.a_x_hi, w.a_x_lo, Mx, eq, &pr[np++]));
+      STK_TRY(lintc2(e, pr, np, s));
       AttnOut ao;
       ao.split = Kc; ao.ld = D;
       ao.hi_a = w.attn_c_hi; ao.lo_a = w.attn_c_lo; ao.hi_b = w.attn_x_hi; ao.lo_b = w.attn_x_lo;
@@ -708,31 +921,31 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       Epilogue erx, erc;
       erx.mode = EPI_RESID; erx.out = w.x; erx.resid = w.x; erx.ldo = D; erx.gate = xmod + 2 * D; erx.gate_ld = 6 * D; erx.gate_period = 1;
       erc.mode = EPI_RESID; erc.out = w.ctx; erc.resid = w.ctx; erc.ldo = D; erc.gate = cmod + 2 * D; erc.gate_ld = 6 * D; erc.gate_period = Kc;
-      int np = 0;
-      if (!last) STK_TRY(tc_problem(e, pc + "attn.proj", w.attn_c_hi, w.attn_c_lo, Mc, erc, &pr[np++]));
+      np = 0;
+      if (ctx_post) STK_TRY(tc_problem(e, pc + "attn.proj", w.attn_c_hi, w.attn_c_lo, Mc, erc, &pr[np++]));
       STK_TRY(tc_problem(e, px + "attn.proj", w.attn_x_hi, w.attn_x_lo, Mx, erx, &pr[np++]));
       STK_TRY(lintc2(e, pr, np, s));
       lp[0].shift = cmod + 3 * D; lp[0].scale = cmod + 4 * D; lp[0].ld_mod = 6 * D; lp[0].period = Kc;
       lp[1].shift = xmod + 3 * D; lp[1].scale = xmod + 4 * D;
-      if (!last) PROF(PC_LN, launch_ln_mod_pair(lp, 2, D, 1e-6f, s, fp16));
+      if (ctx_post) PROF(PC_LN, launch_ln_mod_pair(lp, 2, D, 1e-6f, s, fp16));
       else PROF(PC_LN, launch_ln_mod_pair(lp + 1, 1, D, 1e-6f, s, fp16));
       Epilogue ehc, ehx;
       ehc.mode = EPI_SPLIT; ehc.act = ACT_GELU; ehc.out_hi = w.h_c_hi; ehc.out_lo = w.h_c_lo; ehc.ldo = 4 * D;
       ehx = ehc; ehx.out_hi = w.h_x_hi; ehx.out_lo = w.h_x_lo;
       np = 0;
-      if (!last) STK_TRY(tc_problem(e, pc + "mlp.fc1", w.a_c_hi, w.a_c_lo, Mc, ehc, &pr[np++]));
+      if (ctx_post) STK_TRY(tc_problem(e, pc + "mlp.fc1", w.a_c_hi, w.a_c_lo, Mc, ehc, &pr[np++]));
       STK_TRY(tc_problem(e, px + "mlp.fc1", w.a_x_hi, w.a_x_lo, Mx, ehx, &pr[np++]));
       STK_TRY(lintc2(e, pr, np, s));
       erc.gate = cmod + 5 * D; erx.gate = xmod + 5 * D;
       np = 0;
-      if (!last) STK_TRY(tc_problem(e, pc + "mlp.fc2", w.h_c_hi, w.h_c_lo, Mc, erc, &pr[np++]));
+      if (ctx_post) STK_TRY(tc_problem(e, pc + "mlp.fc2", w.h_c_hi, w.h_c_lo, Mc, erc, &pr[np++]));
       STK_TRY(tc_problem(e, px + "mlp.fc2", w.h_x_hi, w.h_x_lo, Mx, erx, &pr[np++]));
       STK_TRY(lintc2(e, pr, np, s));
       continue;
     }
-    if (!last) {
+    if (ctx && !last) {
       STK_TRY(pre_attention(e, pc, w.ctx, Mc, cmod, cmod + D, 6 * D, Kc, w.a_c, w.a_c_hi, w.a_c_lo, Kc, S, 0, s));
-    } else {
+    } else if (ctx) {
       const float* lm = e->ctx_last_mod + (int64_t)step * 2 * D;                // pre_only: (shift, scale) from c
       STK_TRY(pre_attention(e, pc, w.ctx, Mc, lm, lm + D, 2 * D, 1, w.a_c, w.a_c_hi, w.a_c_lo, Kc, S, 0, s));
     }
@@ -749,17 +962,17 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
       ao.fp16 = is_fp16(e);
       PROF(PC_ATTN, launch_attention_tc5(w.qkv_hi, B, S, e->H, ctx_rows, ctx_keys, ao, s, is_fp16(e), nsplit(e) == 3 ? w.qkv_lo : nullptr));
     }
-    if (!last)
+    if (ctx_post)
       STK_TRY(post_attention(e, pc, w.ctx, Mc, cmod, 6 * D, Kc, w.attn_c, w.attn_c_hi, w.attn_c_lo, w.a_c, w.a_c_hi, w.a_c_lo,
                              w.h_c, w.h_c_hi, w.h_c_lo, s));
     STK_TRY(post_attention(e, px, w.x, Mx, xmod, 6 * D, 1, w.attn_x, w.attn_x_hi, w.attn_x_lo, w.a_x, w.a_x_hi, w.a_x_lo,
                            w.h_x, w.h_x_hi, w.h_x_lo, s));
   }
   // FinalLayer (mmdit.py:641-645): fp32 FFMA (N = p*p*C = 64 columns)
-  const float* fm = e->final_mod + (int64_t)step * 2 * D;
+  const float* fm = (uncond ? e->final_mod_u : e->final_mod) + (int64_t)step * 2 * D;
   PROF(PC_LN, launch_ln_mod(w.x, D, fm, fm + D, 2 * D, 1, w.a_x, nullptr, nullptr, D, Mx, D, 1e-6f, s));
   Epilogue ep;
-  ep.out = w.o_final;
+  ep.out = o_out ? o_out : w.o_final;
   return lin32(e, "model.final_layer.linear", w.a_x, D, Mx, ep, s);
 }
 
@@ -788,15 +1001,40 @@ static int dit_forward(selftok_engine* e, int B, int step, cudaStream_t s) {
   return joint_blocks(e, B, Kc, step, /*ctx_self=*/e->cfg.context_see_xt == 0, s);
 }
 
-static int decode_body(selftok_engine* e, int B, int steps, cudaStream_t s) {
+// The two evaluations of one guided step (sample_one_step with cfg_scale != 1, rectified_flow.py:280-289): the conditional
+// one -- called there WITHOUT context_see_xt, i.e. context rows only see the visible context keys -- into ws.o_final, and
+// MMDiT.cfg_inference (context = zeros, every context key masked for every row: the image stream alone, integer timestep)
+// into ws.o_final_u.
+static int dit_forward_cfg(selftok_engine* e, int B, int step, cudaStream_t s) {
+  const selftok_config_t& c = e->cfg;
+  DecodeWs& w = e->dws;
+  const int D = e->D, N = e->Nimg, Kc = e->k[step] + 1;
+  STK_CHECK(e->has_cfg, SELFTOK_ERR_STATE, "guided sampling needs selftok_set_cfg_schedule before selftok_finalize");
+  PROF(PC_OTHER, launch_patchify(w.x_lat, w.patch, B, c.in_channels, c.latent, c.latent, c.dit_patch, s));
+  Epilogue ep;
+  ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
+  STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
+  PROF(PC_OTHER, launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
+  STK_TRY(joint_blocks(e, B, Kc, step, /*ctx_self=*/true, s, /*uncond=*/false, w.o_final));
+  STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
+  return joint_blocks(e, B, 0, step, /*ctx_self=*/false, s, /*uncond=*/true, w.o_final_u);
+}
+
+static int decode_body(selftok_engine* e, int B, int steps, cudaStream_t s, bool guided = false, float cfg_scale = 1.f) {
   const selftok_config_t& c = e->cfg;
   DecodeWs& w = e->dws;
   STK_TRY(run_lookup(e, w.tokens, B, w.outs_q, s));
   STK_TRY(context_embed(e, B, s));
   for (int i = 0; i < steps; ++i) {
-    STK_TRY(dit_forward(e, B, i, s));
     // euler_step (rectified_flow.py:301-303): x <- x - (t_i - t_{i+1}) * v, fused with unpatchify
-    PROF(PC_OTHER, launch_unpatchify_axpy(w.o_final, w.x_lat, w.x_lat, e->dt[i], B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+    if (!guided) {
+      STK_TRY(dit_forward(e, B, i, s));
+      PROF(PC_OTHER, launch_unpatchify_axpy(w.o_final, w.x_lat, w.x_lat, e->dt[i], B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s));
+    } else {
+      STK_TRY(dit_forward_cfg(e, B, i, s));
+      PROF(PC_OTHER, launch_unpatchify_axpy(w.o_final, w.x_lat, w.x_lat, e->dt[i], B, c.in_channels, c.latent / c.dit_patch, c.dit_patch, s,
+                                            w.o_final_u, cfg_scale));
+    }
   }
   return 0;
 }
@@ -807,9 +1045,25 @@ extern "C" __attribute__((visibility("default"))) int selftok_set_use_graph(self
   return SELFTOK_OK;
 }
 
+static int decode_impl(selftok_handle_t e, const int64_t* tokens_dev, const float* noise_dev, int B, int steps, float* x0_out_dev,
+                       void* stream, bool guided, float cfg_scale);
+
 extern "C" __attribute__((visibility("default"))) int selftok_decode(selftok_handle_t e, const int64_t* tokens_dev, const float* noise_dev, int B, int steps,
                               float* x0_out_dev, void* stream) {
+  return decode_impl(e, tokens_dev, noise_dev, B, steps, x0_out_dev, stream, false, 1.f);
+}
+
+// Guided sampler: p_sample_loop(..., uncond_scale = cfg_scale) of the reference (rectified_flow.py:165-294): two MMDiT
+// evaluations per step, v = v_u + cfg_scale (v_c - v_u).  Needs selftok_set_cfg_schedule before finalize.
+extern "C" __attribute__((visibility("default"))) int selftok_decode_cfg(selftok_handle_t e, const int64_t* tokens_dev, const float* noise_dev, int B, int steps,
+                                  float cfg_scale, float* x0_out_dev, void* stream) {
+  return decode_impl(e, tokens_dev, noise_dev, B, steps, x0_out_dev, stream, true, cfg_scale);
+}
+
+static int decode_impl(selftok_handle_t e, const int64_t* tokens_dev, const float* noise_dev, int B, int steps, float* x0_out_dev,
+                       void* stream, bool guided, float cfg_scale) {
   HOT_PROLOGUE(e);
+  STK_CHECK(!guided || e->has_cfg, SELFTOK_ERR_STATE, "selftok_decode_cfg: selftok_set_cfg_schedule was not called before finalize");
   STK_CHECK(tokens_dev && noise_dev && x0_out_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_decode: bad argument");
   STK_CHECK(!e->cfg.renderer, SELFTOK_ERR_STATE, "handle was created for the renderer; use selftok_render");
   STK_CHECK(steps > 0 && steps <= e->steps, SELFTOK_ERR_BAD_ARG, "steps exceeds the schedule");
@@ -818,8 +1072,8 @@ extern "C" __attribute__((visibility("default"))) int selftok_decode(selftok_han
   const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
   if (tokens_dev != w.tokens) STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_dev, sizeof(int64_t) * B * e->cfg.K, cudaMemcpyDeviceToDevice, s));
   if (noise_dev != w.x_lat) STK_CUDA(cudaMemcpyAsync(w.x_lat, noise_dev, sizeof(float) * nlat, cudaMemcpyDeviceToDevice, s));
-  if (!e->use_graph) {
-    STK_TRY(decode_body(e, B, steps, s));
+  if (!e->use_graph || guided) {          // the guided loop takes cfg_scale as a kernel argument: launched eagerly, not captured
+    STK_TRY(decode_body(e, B, steps, s, guided, cfg_scale));
     e->last_launches = g_launch_count - launches0;
   } else {
     auto key = std::make_pair(B, steps);

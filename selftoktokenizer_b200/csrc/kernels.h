@@ -79,8 +79,9 @@ int launch_lookup_ln3(const int64_t* ids, int64_t R, const float* codebook, int 
 // [B,C,Hh,Ww] latents -> [B*(Hh/p)*(Ww/p), C*p*p] patch rows ((c,ph,pw) fastest-last, Conv2d weight order)
 int launch_patchify(const float* x, float* out, int B, int C, int Hh, int Ww, int p, cudaStream_t s);
 // x_lat[b,c,h*p+ph,w*p+pw] = x_in[...] - dt * o[b, h*g+w, (ph*p+pw)*C + c]   (unpatchify + Euler; dt = -1 & x_in NULL: plain unpatchify)
+// o_u != NULL (guided sampler): v = o_u + cfg_scale * (o - o_u) first
 int launch_unpatchify_axpy(const float* o, const float* x_in, float* x_out, float dt, int B, int C, int g, int p,
-                           cudaStream_t s);
+                           cudaStream_t s, const float* o_u = nullptr, float cfg_scale = 1.f);
 int launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t s);
 int launch_split_bf16(const float* in, __nv_bfloat16* hi, __nv_bfloat16* lo, int64_t n, cudaStream_t s, int fp16 = 0);
 // out[b, r, :] = src[r, :] for b in 0..B-1 (broadcast rows), optionally + add[r,:]

@@ -809,23 +809,26 @@ int launch_patchify(const float* x, float* out, int B, int C, int Hh, int Ww, in
 
 // unpatchify (sd3/mmdit.py:898-916: x.reshape(N,h,w,p,p,c) -> 'nhwpqc->nchpwq') fused with the Euler update
 // x_prev = x - (a_t - a_prev) * v (sd3/rectified_flow.py:303).
+// Guided sampler (rectified_flow.py:280-289): with o_u the velocity is  v = v_u + cfg_scale * (v_c - v_u)  before the update.
 __global__ void unpatchify_axpy_kernel(const float* __restrict__ o, const float* __restrict__ x_in, float* __restrict__ x_out,
-                                       float dt, int B, int C, int g, int p) {
+                                       float dt, int B, int C, int g, int p, const float* __restrict__ o_u, float cfg_scale) {
   const int Hh = g * p;
   const int64_t total = (int64_t)B * C * Hh * Hh;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int xw = (int)(i % Hh); int64_t t = i / Hh;
     int yh = (int)(t % Hh); t /= Hh; int c = (int)(t % C); int b = (int)(t / C);
     int h = yh / p, ph = yh % p, w = xw / p, pw = xw % p;
-    float v = o[((int64_t)b * g * g + h * g + w) * (p * p * C) + (ph * p + pw) * C + c];
+    const int64_t oi = ((int64_t)b * g * g + h * g + w) * (p * p * C) + (ph * p + pw) * C + c;
+    float v = o[oi];
+    if (o_u) { const float vu = o_u[oi]; v = vu + cfg_scale * (v - vu); }
     x_out[i] = x_in ? (x_in[i] - dt * v) : v;
   }
 }
 int launch_unpatchify_axpy(const float* o, const float* x_in, float* x_out, float dt, int B, int C, int g, int p,
-                           cudaStream_t s) {
+                           cudaStream_t s, const float* o_u, float cfg_scale) {
   STK_CHECK(o && x_out, -1, "unpatchify: bad arguments");
   int64_t total = (int64_t)B * C * g * p * g * p;
-  unpatchify_axpy_kernel<<<(unsigned)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, s>>>(o, x_in, x_out, dt, B, C, g, p);
+  unpatchify_axpy_kernel<<<(unsigned)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256), 256, 0, s>>>(o, x_in, x_out, dt, B, C, g, p, o_u, cfg_scale);
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;

@@ -18,6 +18,7 @@ buffers are not incremented; no host syncs inside the loop.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -84,19 +85,63 @@ def _decoder_state(state_dict: Dict, ema_decoder: bool) -> Dict[str, torch.Tenso
     return sd
 
 
+class ImageTokenizerShell:
+    """`pipeline.model` of the reference is the ImageTokenizer nn.Module (SelftokPipeline.py:168-199): users reach for
+    `state_dict()` / `load_state_dict()` / `eval()` on it.  The arithmetic lives in the CUDA engine, so this shell only keeps the
+    checkpoint interface: `state_dict()` returns the tensors the engine was built from (re-read from `ckpt_path` when the engine
+    came from the prepack cache), `load_state_dict()` rebuilds the engine from new weights and reports missing / unexpected keys
+    against the path's state-dict contract (synth.state_dict_spec)."""
+
+    def __init__(self, pipeline: "SelftokPipeline", state_dict):
+        self._p = pipeline
+        self._sd = state_dict
+
+    def state_dict(self):
+        if self._sd is None:
+            self._sd = self._p._read_checkpoint()
+        return {k: v for k, v in self._sd.items() if torch.is_tensor(v)}
+
+    def load_state_dict(self, state_dict, strict: bool = False):
+        from .synth import state_dict_spec
+        spec = state_dict_spec(self._p.dims)
+        missing = [k for k in spec if k not in state_dict]
+        unexpected = [k for k in state_dict if torch.is_tensor(state_dict[k]) and (k.startswith("encoder.") or k.startswith("model."))
+                      and k not in spec and not k.startswith("model.y_embedder.")]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"Error(s) in loading state_dict: missing {missing[:5]}..., unexpected {unexpected[:5]}...")
+        if missing:
+            raise SelftokError(f"checkpoint lacks tensors the path needs: {missing[:5]} ...")
+        self._p._build_engine(state_dict, pack_path=None)
+        self._sd = state_dict
+        return missing, unexpected
+
+    def eval(self):
+        return self
+
+    def to(self, *a, **k):
+        return self
+
+    def cuda(self, *a, **k):
+        return self
+
+
 class SelftokPipeline:
     def __init__(self, cfg, ckpt_path, sd3_path, datasize=256, start=1.0, cfg_scale=1, model_type="sd3",
                  dtype=torch.bfloat16, ema_decoder=False, device=None, *, state_dict=None, vae=None,
-                 precision="auto", dims: Optional[SelftokDims] = None):
+                 precision="auto", dims: Optional[SelftokDims] = None, prepack_cache: Optional[str] = None):
+        """Same positional signature as the reference (SelftokPipeline.py:154).  Keyword-only extras: `state_dict` (in-memory
+        checkpoint), `vae` (any object with the diffusers encode / decode call shape), `precision`, `dims`, and `prepack_cache`
+        = a directory for the engine's packed device state: the second construction on the same checkpoint file skips
+        torch.load, the uploads, the table MLPs and the operand packing."""
         self.cfg = cfg
         self.datasize = datasize
         self.model_type = model_type
         self.dtype = dtype
         if self.model_type != "sd3":
             raise ValueError(f"Unsupported MODEL_TYPE: {self.model_type}. Expected 'sd3'")
-        if cfg_scale != 1:
-            raise SelftokError("cfg_scale != 1 is not on the shipped path (the reference never forwards it: "
-                               "rectified_flow.py:173 default uncond_scale=1.0)")
+        # cfg_scale is stored and -- exactly as in the reference (SelftokPipeline.py:181 stores it, p_sample_loop is called
+        # without uncond_scale: rectified_flow.py:173 default 1.0) -- NOT used by decoding(); the guided sampler the reference
+        # implements in RectifiedFlow.sample_one_step is reachable through decode_latents(..., cfg_scale=...) / decoding_cfg().
         self.device = torch.device(device if device is not None else "cuda")
         # `datasize` (a CLI argument of the reference's test.py) sets the latent side: the models are built from the cfg but
         # run at datasize // 8 through the centre-cropped positional grids (models_ours.py:183-202, sd3/mmdit.py:877-896)
@@ -121,16 +166,42 @@ class SelftokPipeline:
         self.cut_of_k = p.get("cut_of_k", None) or None
         if self.cut_of_k is not None:
             raise SelftokError("cut_of_k is not on the shipped path")
-        if state_dict is None:
-            state_dict = torch.load(ckpt_path, map_location="cpu")
-        print("Loading all...")
+        self.ckpt_path = ckpt_path
+        self._precision_req = precision
         self._steps = 50
-        self.engine = Engine(self.dims, _decoder_state(state_dict, ema_decoder), device=self.device,
-                             precision=precision, steps=self._steps, start=self.start)
+        pack_path = None
+        if prepack_cache and ckpt_path and os.path.exists(ckpt_path):
+            import hashlib
+            st = os.stat(ckpt_path)
+            key = hashlib.sha1(repr((os.path.abspath(ckpt_path), st.st_size, st.st_mtime_ns, self.dims, precision, self._steps,
+                                     float(start), bool(ema_decoder))).encode()).hexdigest()[:20]
+            os.makedirs(prepack_cache, exist_ok=True)
+            pack_path = os.path.join(prepack_cache, f"selftok_{key}.stkpack")
+        print("Loading all...")
+        self.engine = None
+        if pack_path and os.path.exists(pack_path) and os.path.exists(pack_path + ".json") and state_dict is None:
+            self._build_engine(None, pack_path)                      # no torch.load at all
+        else:
+            if state_dict is None:
+                state_dict = self._read_checkpoint()
+            self._build_engine(state_dict, pack_path)
+        self.model = ImageTokenizerShell(self, state_dict)
         self.diti = sched.DiTiCont(1000, self.dims.K, self.dims.stages, self.dims.k_per_stage)
         self.flow = self.engine.tables           # scheduled t / dt / k tables (RectifiedFlow.make_schedule equivalent)
         self.cond_vary = True
         self.saved_images = 8
+
+    def _read_checkpoint(self):
+        return torch.load(self.ckpt_path, map_location="cpu")        # SelftokPipeline.py:190
+
+    def _build_engine(self, state_dict, pack_path) -> None:
+        sd = None if state_dict is None else _decoder_state(state_dict, self.ema_decoder)
+        new = Engine(self.dims, sd, device=self.device, precision=self._precision_req, steps=self._steps, start=self.start,
+                     pack_path=pack_path)
+        if self.engine is not None:
+            self.engine.close()
+        self.engine = new
+        self.flow = self.engine.tables
 
     # ------------------------------------------------------------------ latent-boundary API (the measured path)
     @torch.no_grad()
@@ -139,15 +210,20 @@ class SelftokPipeline:
         return self.engine.encode(x_0)
 
     @torch.no_grad()
-    def decode_latents(self, idx, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def decode_latents(self, idx, noise: Optional[torch.Tensor] = None, cfg_scale: Optional[float] = None) -> torch.Tensor:
         """tokens -> pred_x0 latents after the 50-step Euler loop.  `noise` defaults to the reference's draw:
-        torch.randn on the CPU global generator, then moved to the device (SelftokPipeline.py:262-264)."""
+        torch.randn on the CPU global generator, then moved to the device (SelftokPipeline.py:262-264).
+        cfg_scale (None / 1: plain sampler): classifier-free guidance as RectifiedFlow.sample_one_step implements it
+        (rectified_flow.py:280-289) -- an explicit argument here because the reference pipeline never forwards its own."""
         token_idx = torch.from_numpy(idx) if isinstance(idx, np.ndarray) else idx
         B = token_idx.shape[0]
         latent_dim = self.datasize // 8
         if noise is None:
             noise = torch.randn(B, self.dims.in_channels, latent_dim, latent_dim)
-        out = self.engine.decode(token_idx, noise)
+        if cfg_scale is None or float(cfg_scale) == 1.0:
+            out = self.engine.decode(token_idx, noise)
+        else:
+            out = self.engine.decode_cfg(token_idx, noise, float(cfg_scale))
         self._raise_on_bad_ids(token_idx)
         return out
 
@@ -189,6 +265,15 @@ class SelftokPipeline:
         recons = self.vae.decode(pred_x0_out, return_dict=False)[0]
         norm_ip(recons, -1, 1)
         print("End decoding.")
+        return recons
+
+    @torch.no_grad()
+    def decoding_cfg(self, idx, device, cfg_scale: Optional[float] = None):
+        """decoding() with the guided sampler (cfg_scale defaults to the constructor's)."""
+        self._need_vae()
+        pred_x0 = self.decode_latents(idx, cfg_scale=self.cfg_scale if cfg_scale is None else cfg_scale)
+        recons = self.vae.decode(SD3LatentFormat().process_out(pred_x0).to(self.dtype), return_dict=False)[0]
+        norm_ip(recons, -1, 1)
         return recons
 
     @torch.no_grad()

@@ -17,7 +17,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -73,6 +73,7 @@ class SamplerTables:
     k: torch.Tensor          # [steps] int64, last visible context index
     t_freq: torch.Tensor     # [steps,256] fp32: timestep_embedding(t*1000) for MMDiT.t_embedder (mmdit.py:1000,1022)
     pos_freq: torch.Tensor   # [K,256]   fp32: timestep_embedding(1000+8k) for pos-indexed adaLN (mmdit.py:446-458; modules.py:311-317)
+    t_freq_uncond: Optional[torch.Tensor] = None   # [steps,256]: features of floor(1000 t).int().clamp(0,999) (MMDiT.cfg_inference, mmdit.py:1127)
 
 
 def make_tables(K: int, stages: Sequence[int], k_per_stage: Sequence[int], steps: int = 50,
@@ -88,8 +89,10 @@ def make_tables(K: int, stages: Sequence[int], k_per_stage: Sequence[int], steps
     t_freq = timestep_embedding(scheduled_t * 1000.0)
     # get_position(torch.arange(K)) is int64 -> .float() inside timestep_embedding
     pos_freq = timestep_embedding(DiTiCont.get_position(torch.arange(K)))
+    # the unconditional branch of the guided sampler embeds an INTEGER timestep (mmdit.py:1127): floor(t*1000).int().clamp(0,999)
+    t_freq_uncond = timestep_embedding(torch.floor(scheduled_t * 1000).int().clamp(0, 999))
     return SamplerTables(steps=steps, t=scheduled_t.clone(), dt=(scheduled_t - scheduled_t_prev),
-                         t_mapped=t_mapped, k=k, t_freq=t_freq, pos_freq=pos_freq)
+                         t_mapped=t_mapped, k=k, t_freq=t_freq, pos_freq=pos_freq, t_freq_uncond=t_freq_uncond)
 
 
 def renderer_t_freq() -> torch.Tensor:

@@ -289,3 +289,12 @@ def test_mid_fixture_oracle(gold):
     assert np.array_equal(tok.numpy(), g["tokens"])
     x = O.decode(sd, d, tok, torch.from_numpy(g["noise"]), truncate=True)
     assert np.abs(x.numpy() - g["pred_x0"]).max() < 2e-5
+
+
+def test_oracle_guided_sampler_matches_reference_fixture(gold, tiny_sd):
+    """f3: the restatement of sample_one_step's guided branch + MMDiT.cfg_inference against the reference's own
+    p_sample_loop(..., uncond_scale=2.5) (tests/golden/tiny_cfg.npz)."""
+    g, gc = gold("tiny"), gold("tiny_cfg")
+    x = O.decode_cfg(tiny_sd, C.TINY, torch.from_numpy(g["tokens"]), torch.from_numpy(g["noise"]), float(gc["cfg_scale"]))
+    assert np.abs(x.numpy() - gc["pred_x0"]).max() < 2e-5
+    assert np.abs(gc["pred_x0"] - g["pred_x0"]).max() > 0.05          # the guidance really changes the result

@@ -501,3 +501,67 @@ def test_full_renderer_1024_tokens(gold):
     assert tuple(tok.shape) == (2, 1024) and int(tok.min()) >= 0 and int(tok.max()) < d.codebook_size
     assert torch.equal(tok, eng.encode(x0)) and (tok[0] != tok[1]).float().mean() > 0.3
     eng.close()
+
+
+def test_prepack_cache_and_model_shell(tiny_sd, gold, tmp_path):
+    """f2: checkpoint file -> engine -> prepack cache -> second engine WITHOUT torch.load: identical tokens and latents
+    (bitwise); `pipeline.model` keeps the checkpoint interface (state_dict / load_state_dict), EMA decoder selection included."""
+    import copy
+    from selftoktokenizer_b200 import SelftokPipeline
+    from selftoktokenizer_b200.capi import SelftokError
+    g = gold("tiny")
+    d = C.TINY
+    ckpt = dict(tiny_sd)
+    ema = {k[len("model."):]: v * 1.01 for k, v in tiny_sd.items() if k.startswith("model.")}     # a different decoder
+    ckpt["ema_state_dict"] = ema
+    path = str(tmp_path / "tokenizer_ckpt.pth")
+    torch.save(ckpt, path)
+    cache = str(tmp_path / "cache")
+    kw = dict(cfg=None, sd3_path=None, datasize=d.latent * 8, device=DEV, dims=d, precision="fp16")
+    p1 = SelftokPipeline(ckpt_path=path, prepack_cache=cache, **kw)
+    assert not p1.engine.restored_from_pack and len([f for f in __import__("os").listdir(cache) if f.endswith(".stkpack")]) == 1
+    x0 = synth.synth_tensor("golden.tiny.x0", (3, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    noise = torch.from_numpy(g["noise"])
+    t1, x1 = p1.encode_latents(x0).cpu(), p1.decode_latents(g["tokens"], noise=noise).cpu()
+    real_load = torch.load
+    try:
+        torch.load = lambda *a, **k: (_ for _ in ()).throw(AssertionError("torch.load called although the prepack cache is warm"))
+        p2 = SelftokPipeline(ckpt_path=path, prepack_cache=cache, **kw)
+    finally:
+        torch.load = real_load
+    assert p2.engine.restored_from_pack
+    assert torch.equal(p2.encode_latents(x0).cpu(), t1) and torch.equal(p2.decode_latents(g["tokens"], noise=noise).cpu(), x1)
+    _check_tokens(t1.numpy(), g["tokens"], g["margin"], "prepack encode")
+    assert np.abs(x1.numpy() - g["pred_x0"]).max() < TOL["fp16"]
+    # the module shell: state_dict round trip and a reload that changes the decoder
+    sd = p2.model.state_dict()                                       # read from the checkpoint file on demand
+    assert set(k for k in sd if k.startswith("encoder.") or k.startswith("model.")) >= set(synth.state_dict_spec(d))
+    sd2 = copy.copy(sd)
+    sd2["model.final_layer.linear.bias"] = sd["model.final_layer.linear.bias"] + 0.5
+    missing, unexpected = p2.model.load_state_dict(sd2)
+    assert missing == [] and unexpected == []
+    assert not torch.equal(p2.decode_latents(g["tokens"], noise=noise).cpu(), x1)
+    with pytest.raises(SelftokError):
+        p2.model.load_state_dict({k: v for k, v in sd.items() if k != "model.context_pos_embed"})
+    # EMA decoder (SelftokPipeline.py:193-199): another cache key, another result
+    p3 = SelftokPipeline(ckpt_path=path, prepack_cache=cache, ema_decoder=True, **kw)
+    assert not p3.engine.restored_from_pack
+    assert torch.equal(p3.encode_latents(x0).cpu(), t1)
+    assert not torch.equal(p3.decode_latents(g["tokens"], noise=noise).cpu(), x1)
+    for p in (p1, p2, p3):
+        p.engine.close()
+
+
+def test_guided_sampler_cfg(tiny_engine, gold):
+    """f3: classifier-free guidance as RectifiedFlow.sample_one_step implements it (two evaluations per step: conditional with
+    context rows blind to the image keys, unconditional = image stream alone at the integer timestep) against the reference's own
+    p_sample_loop(..., uncond_scale=2.5)."""
+    g, gc = gold("tiny"), gold("tiny_cfg")
+    tok, noise = torch.from_numpy(g["tokens"]), torch.from_numpy(g["noise"])
+    x = tiny_engine.decode_cfg(tok, noise, float(gc["cfg_scale"])).cpu().numpy()
+    err = float(np.abs(x - gc["pred_x0"]).max())
+    print(f"[{tiny_engine.precision}] guided 50-step decode (cfg 2.5): max-abs err {err:.3e}")
+    assert err < 2.5 * TOL[tiny_engine.precision]                      # the combination amplifies the per-evaluation error by ~cfg_scale
+    # scale 1 collapses to the conditional branch alone -- which is NOT decode(): the guided call site drops context_see_xt
+    x1 = tiny_engine.decode_cfg(tok, noise, 1.0, steps=3)
+    assert torch.isfinite(x1).all()
