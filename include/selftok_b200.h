@@ -155,6 +155,19 @@ int selftok_render_host(selftok_handle_t h, const int64_t* tokens_host, int B, f
  * resets it (< 0: CUDA error). */
 int64_t selftok_id_errors(selftok_handle_t h, void* stream);
 
+/* ---- SD3 VAE decoder on the device: replaces `self.vae.decode(pred_x0_out)` of SelftokPipeline.decoding /
+ * decoding_with_renderer (SelftokPipeline.py:288,316; architecture: sd3/sd3_impls.py:314-444).  Weights are loaded under the
+ * in-tree SDVAE key names ("decoder.conv_in.weight", "decoder.up.3.block.0.norm1.bias", ...), fp32, one call per tensor.
+ * selftok_vae_decode: z_dev [B,16,h,w] fp32 in VAE latent space (after SD3LatentFormat.process_out), h = w in {8,16,32,64}
+ * -> out_dev [B,3,8h,8w] fp32; norm_ip != 0 applies the pipeline's clamp to [-1,1] + rescale to [0,1]. */
+typedef struct selftok_vae* selftok_vae_t;
+int selftok_vae_create(int ch /* 128 */, int device, selftok_vae_t* out);
+int selftok_vae_destroy(selftok_vae_t v);
+int selftok_vae_load_tensor(selftok_vae_t v, const char* name, const void* data, int ndim, const int64_t* shape, int is_device);
+int selftok_vae_finalize(selftok_vae_t v, void* stream);
+int selftok_vae_decode(selftok_vae_t v, const float* z_dev, int B, int h, int w, float* out_dev, int norm_ip, void* stream);
+int64_t selftok_vae_device_bytes(selftok_vae_t v);
+
 /* ---- introspection ----------------------------------------------------------------------------------------- */
 /* Number of kernel launches issued (or replayed from a graph) by the last hot-path call on this handle. */
 int64_t selftok_last_launch_count(selftok_handle_t h);

@@ -165,9 +165,9 @@ def gen_vae_tiny():
 
 def gen_pixels_tiny():
     """Pixel fixture of the reduced geometry: the reference's own 50-step result (tests/golden/tiny.npz) through the
-    reference SDVAE (ch = 32) exactly as SelftokPipeline.decoding finishes (process_out -> vae.decode -> norm_ip)."""
+    reference SDVAE (full size, ch = 128) exactly as SelftokPipeline.decoding finishes (process_out -> vae.decode -> norm_ip)."""
     g = np.load(os.path.join(GOLD, "tiny.npz"))
-    vae = ref_vae(32)
+    vae = ref_vae(128)
     save("tiny_pixels", pixels=ref_pixels(vae, torch.from_numpy(g["pred_x0"])))
 
 

@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libselftok_b200.so")
-SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "attn_tc5.cu", "engine.cu"]
+SOURCES = ["kernels_simt.cu", "gemm_tc.cu", "attn_tc5.cu", "engine.cu", "vae.cu"]
 HEADERS = ["common.cuh", "kernels.h", os.path.join("..", "..", "include", "selftok_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -27,6 +27,7 @@ SYMBOLS = [
     "selftok_render_host", "selftok_id_errors", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
     "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_set_gemm_ctas", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
     "selftok_k_attention_tc",
+    "selftok_vae_create", "selftok_vae_destroy", "selftok_vae_load_tensor", "selftok_vae_finalize", "selftok_vae_decode", "selftok_vae_device_bytes",
 ]
 
 
@@ -90,6 +91,13 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.selftok_k_ln_mod_f32.argtypes = [vp, vp, vp, i64, i32, vp, i64, i32, vp]
     lib.selftok_k_attention_f32.argtypes = [vp, i64, vp, vp, i64, i32, vp, vp, i64, i32, vp, i64, i32, i32, i32, i32, vp]
     lib.selftok_k_attention_tc.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, vp]
+    lib.selftok_vae_create.argtypes = [i32, i32, C.POINTER(vp)]
+    lib.selftok_vae_destroy.argtypes = [vp]
+    lib.selftok_vae_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
+    lib.selftok_vae_finalize.argtypes = [vp, vp]
+    lib.selftok_vae_decode.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp]
+    lib.selftok_vae_device_bytes.argtypes = [vp]
+    lib.selftok_vae_device_bytes.restype = i64
     for name in SYMBOLS:
         getattr(lib, name)          # AttributeError here == header / library drift
     _lib = lib
@@ -406,6 +414,85 @@ class Engine:
     def close(self) -> None:
         if getattr(self, "h", None):
             self.lib.selftok_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VaeDecoder:
+    """SD3 VAE decoder on the device (`selftok_vae_t`): the `vae.decode` step of SelftokPipeline.decoding.  `state_dict` uses the
+    in-tree SDVAE key names (decoder.*); `from_diffusers_keys` maps a diffusers AutoencoderKL state dict onto them."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", ch: int = 128):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise SelftokError("no CUDA device: selftok_b200 has no CPU fallback")
+        self.device = torch.device(device)
+        h = C.c_void_p()
+        check(self.lib.selftok_vae_create(ch, self.device.index or 0, C.byref(h)))
+        self.h = h
+        try:
+            for name, t in state_dict.items():
+                if not name.startswith("decoder.") or not torch.is_tensor(t):
+                    continue
+                t = t.detach().to(torch.float32).contiguous()
+                if t.is_cuda and t.device != self.device:
+                    t = t.to(self.device)
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                check(self.lib.selftok_vae_load_tensor(self.h, name.encode(), t.data_ptr(), t.dim(), shape, int(t.is_cuda)))
+            with torch.cuda.device(self.device):
+                check(self.lib.selftok_vae_finalize(self.h, _stream_ptr(self.device)))
+        except Exception:
+            self.close()
+            raise
+
+    def decode(self, z: torch.Tensor, norm_ip: bool = False) -> torch.Tensor:
+        """z [B,16,h,w] (VAE latent space) -> [B,3,8h,8w] fp32 on the device."""
+        if z.dim() != 4 or z.shape[1] != 16 or z.shape[2] != z.shape[3]:
+            raise SelftokError(f"VaeDecoder.decode: expected [B,16,h,h] latents, got {tuple(z.shape)}")
+        z = z.to(device=self.device, dtype=torch.float32).contiguous()
+        B, _, h, w = z.shape
+        out = torch.empty(B, 3, 8 * h, 8 * w, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_vae_decode(self.h, z.data_ptr(), B, h, w, out.data_ptr(), int(norm_ip), _stream_ptr(self.device)))
+        return out
+
+    @staticmethod
+    def from_diffusers_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        """diffusers AutoencoderKL decoder keys -> SDVAE keys (the same weights under the other naming: up_blocks are listed
+        lowest resolution first there, attention projections are Linear [C,C] instead of 1x1 convs)."""
+        out = {}
+        ren = {"conv_norm_out": "norm_out", "mid_block.resnets.0": "mid.block_1", "mid_block.resnets.1": "mid.block_2",
+               "mid_block.attentions.0.group_norm": "mid.attn_1.norm", "mid_block.attentions.0.to_q": "mid.attn_1.q",
+               "mid_block.attentions.0.to_k": "mid.attn_1.k", "mid_block.attentions.0.to_v": "mid.attn_1.v",
+               "mid_block.attentions.0.to_out.0": "mid.attn_1.proj_out"}
+        for k, v in sd.items():
+            if not k.startswith("decoder."):
+                continue
+            n = k[len("decoder."):]
+            for a, b in ren.items():
+                if n.startswith(a + "."):
+                    n = b + n[len(a):]
+            if n.startswith("up_blocks."):
+                parts = n.split(".")
+                lvl = 3 - int(parts[1])
+                if parts[2] == "resnets":
+                    n = f"up.{lvl}.block.{parts[3]}." + ".".join(parts[4:])
+                elif parts[2] == "upsamplers":
+                    n = f"up.{lvl}.upsample." + ".".join(parts[4:])
+            n = n.replace("conv_shortcut", "nin_shortcut")
+            if ".attn_1." in n and n.endswith(".weight") and v.dim() == 2:
+                v = v[:, :, None, None]
+            out["decoder." + n] = v
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.lib.selftok_vae_destroy(self.h)
             self.h = None
 
     def __del__(self):

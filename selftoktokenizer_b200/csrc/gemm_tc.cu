@@ -259,6 +259,11 @@ struct GemmParams {
   int N, K;
   int fp16;
   Epilogue ep;
+  // implicit-GEMM 3x3 convolution (stride 1, zero padding 1) over NHWC activations: A row m = output pixel (b, y, x), K index =
+  // tap * C + c.  conv_C == 0: plain GEMM.  The A tile of k-block kb (tap = kb / (C / 64), channels chunk = kb % (C / 64)) is the
+  // 4-D TMA box {64 channels, bw pixels, bh rows, bn images} (bw bh bn = 128) shifted by the tap offset; out-of-image elements
+  // are zero-filled by the TMA unit -- exactly the padding.
+  int conv_C = 0, conv_H = 0, conv_W = 0;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
@@ -437,6 +442,11 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d_2sm_hint(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1,
                                                      uint64_t policy) {
   asm volatile(
@@ -540,20 +550,34 @@ gemm_tc2_kernel(const __grid_constant__ TcMaps maps0, const __grid_constant__ Tc
         int pm, n_blk;
         if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, pm, n_blk);
         else pair_coords(t, pm_tiles0, n_tiles0, pm, n_blk);
-        const int nk = ((second ? p1.K : p0.K) + BK - 1) / BK;
+        const GemmParams& pp = second ? p1 : p0;
+        const int nk = (pp.K + BK - 1) / BK;
         const int m_row = pm * 2 * BM + (int)rank * BM;            // this CTA's 128 A rows
         const int n_row = n_blk * BN + (int)rank * (BN / 2);       // this CTA's half of the W tile
+        // convolution: the 128 rows are 128 / bw image rows of bw pixels starting at (cb, cy, cx)
+        const int chunks = pp.conv_C > 0 ? pp.conv_C / BK : 1;
+        int cx = 0, cy = 0, cb = 0;
+        if (pp.conv_C > 0) {
+          cx = m_row % pp.conv_W;
+          cy = (m_row / pp.conv_W) % pp.conv_H;
+          cb = m_row / (pp.conv_W * pp.conv_H);
+        }
         for (int kb = 0; kb < nk; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t fb = full_bar(stage) & 0xFEFFFFFFu;       // leader's barrier (peer bit cleared)
           if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
-          tma_load_2d_2sm(sa, &mp.a_hi, fb, kb * BK, m_row);
-          tma_load_2d_2sm_hint(sa + C::PLANES * A_TILE_BYTES, &mp.b_hi, fb, kb * BK, n_row, w_policy);
-          if (NSPLIT == 3) {
-            tma_load_2d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, kb * BK, m_row);
-            tma_load_2d_2sm_hint(sa + 2 * A_TILE_BYTES + C::HALF_B_BYTES, &mp.b_lo, fb, kb * BK, n_row, w_policy);
+          if (pp.conv_C > 0) {
+            const int tap = kb / chunks, c0 = (kb - tap * chunks) * BK;
+            const int x0 = cx + tap % 3 - 1, y0 = cy + tap / 3 - 1;
+            tma_load_4d_2sm(sa, &mp.a_hi, fb, c0, x0, y0, cb);
+            if (NSPLIT == 3) tma_load_4d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, c0, x0, y0, cb);
+          } else {
+            tma_load_2d_2sm(sa, &mp.a_hi, fb, kb * BK, m_row);
+            if (NSPLIT == 3) tma_load_2d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, kb * BK, m_row);
           }
+          tma_load_2d_2sm_hint(sa + C::PLANES * A_TILE_BYTES, &mp.b_hi, fb, kb * BK, n_row, w_policy);
+          if (NSPLIT == 3) tma_load_2d_2sm_hint(sa + 2 * A_TILE_BYTES + C::HALF_B_BYTES, &mp.b_lo, fb, kb * BK, n_row, w_policy);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -664,6 +688,26 @@ int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, in
   return 0;
 }
 
+// 4-D map over NHWC 16-bit activations [B][H][W][C] with box {64 channels, bw pixels, bh rows, 128 / (bw bh) images}: 128 output
+// pixels per CTA = part of an image row (W >= 128), whole rows of one image, or -- for images smaller than 128 pixels -- whole images
+int make_map_nhwc(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t B, int H, int W, int Cc, int fp16) {
+  const int bw = W < BM ? W : BM;
+  const int bh = (BM / bw) < H ? (BM / bw) : H;
+  const int bn = BM / (bw * bh);
+  cuuint64_t gdim[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstride[3] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(ptr), gdim, gstride,
+                        box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (NHWC) failed with CUresult " + std::to_string((int)r));
+    return -5;
+  }
+  return 0;
+}
+
 }  // namespace
 
 // Generic 2-D SWIZZLE_128B tensor map over a row-major 16-bit matrix [rows, cols] (box_cols * 2 bytes must be 128).
@@ -722,14 +766,25 @@ static int check_problem(const TcProblem& q, int nsplit, int fp16) {
   STK_CHECK(q.K % 8 == 0, -2, "gemm_tc: K must be a multiple of 8 (16-byte TMA row pitch)");
   STK_CHECK(ep.ldo % 4 == 0 && q.N % 4 == 0, -2, "gemm_tc: N and the output pitch must be multiples of 4");
   STK_CHECK(ep.mode != EPI_RESID || ep.gate == nullptr || ep.gate_ld % 4 == 0, -2, "gemm_tc: gate pitch must be a multiple of 4");
+  if (q.conv_C > 0) {                                      // implicit 3x3 convolution over NHWC planes
+    STK_CHECK(q.conv_C % BK == 0 && q.K == 9 * q.conv_C, -2, "gemm_tc conv: channels must be a multiple of 64 and K = 9 C");
+    STK_CHECK(q.conv_W > 0 && q.conv_H > 0 && (q.conv_W % BM == 0 || BM % q.conv_W == 0), -2, "gemm_tc conv: image width must divide or be a multiple of 128");
+    const int64_t hw = (int64_t)q.conv_H * q.conv_W;
+    STK_CHECK(q.M % hw == 0 && (hw % BM == 0 || BM % hw == 0) && (q.conv_W >= BM || hw < BM || q.conv_H % (BM / q.conv_W) == 0), -2,
+              "gemm_tc conv: 128-pixel tiles must be part of a row, whole rows of one image, or whole images");
+  }
   return 0;
 }
 
 static int make_maps(TcMaps* m, const TcProblem& q, int nsplit, int fp16, int b_box) {
-  STK_TRY(make_map(&m->a_hi, q.A_hi, q.M, q.K, BM, fp16));
+  const bool conv = q.conv_C > 0;
+  const int64_t imgs = conv ? q.M / ((int64_t)q.conv_H * q.conv_W) : 0;
+  if (conv) STK_TRY(make_map_nhwc(&m->a_hi, q.A_hi, imgs, q.conv_H, q.conv_W, q.conv_C, fp16));
+  else STK_TRY(make_map(&m->a_hi, q.A_hi, q.M, q.K, BM, fp16));
   STK_TRY(make_map(&m->b_hi, q.W_hi, q.N, q.K, b_box, fp16));
   if (nsplit == 3) {
-    STK_TRY(make_map(&m->a_lo, q.A_lo, q.M, q.K, BM, fp16));
+    if (conv) STK_TRY(make_map_nhwc(&m->a_lo, q.A_lo, imgs, q.conv_H, q.conv_W, q.conv_C, fp16));
+    else STK_TRY(make_map(&m->a_lo, q.A_lo, q.M, q.K, BM, fp16));
     STK_TRY(make_map(&m->b_lo, q.W_lo, q.N, q.K, b_box, fp16));
   } else {
     m->a_lo = m->a_hi; m->b_lo = m->b_hi;
@@ -747,6 +802,7 @@ int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream
   const int g_num_sms = g_num_sms_dev[dev];
   for (int i = 0; i < n; ++i) STK_TRY(check_problem(probs[i], nsplit, fp16));
   const bool pair = g_gemm_ctas == 2 && g_num_sms >= 2;
+  for (int i = 0; i < n; ++i) STK_CHECK(pair || probs[i].conv_C == 0, -2, "gemm_tc conv: only the SM-pair kernel stages NHWC tiles");
   if (!pair) {                                            // single-CTA bisecting kernel: one launch per problem
     for (int i = 0; i < n; ++i) {
       const TcProblem& q = probs[i];
@@ -764,13 +820,19 @@ int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream
   }
   TcMaps m0, m1;
   STK_TRY(make_maps(&m0, probs[0], nsplit, fp16, BN / 2));
-  GemmParams p0{probs[0].M, probs[0].N, probs[0].K, fp16, probs[0].ep};
-  GemmParams p1{0, probs[0].N, probs[0].K, fp16, probs[0].ep};
+  auto mk_params = [&](const TcProblem& q) {
+    GemmParams g{q.M, q.N, q.K, fp16, q.ep};
+    g.conv_C = q.conv_C; g.conv_H = q.conv_H; g.conv_W = q.conv_W;
+    return g;
+  };
+  GemmParams p0 = mk_params(probs[0]);
+  GemmParams p1 = p0;
+  p1.M = 0;
   m1 = m0;
   int pairs = (int)((probs[0].M + 2 * BM - 1) / (2 * BM)) * ((probs[0].N + BN - 1) / BN);
   if (n == 2) {
     STK_TRY(make_maps(&m1, probs[1], nsplit, fp16, BN / 2));
-    p1 = GemmParams{probs[1].M, probs[1].N, probs[1].K, fp16, probs[1].ep};
+    p1 = mk_params(probs[1]);
     pairs += (int)((probs[1].M + 2 * BM - 1) / (2 * BM)) * ((probs[1].N + BN - 1) / BN);
   }
   const int clusters = pairs < g_num_sms / 2 ? pairs : g_num_sms / 2;

@@ -212,7 +212,7 @@ def test_pixel_fixture_is_reference_latents_through_the_vae_oracle(gold):
     (process_out -> vae.decode -> norm_ip, SelftokPipeline.py:284-294) restated in vae_oracle."""
     import vae_oracle as V
     g, gp = gold("tiny"), gold("tiny_pixels")
-    px = V.images_from_latents(synth.synth_vae_state_dict(ch=32, encoder=False), torch.from_numpy(g["pred_x0"]))
+    px = V.images_from_latents(synth.synth_vae_state_dict(ch=128, encoder=False), torch.from_numpy(g["pred_x0"]))
     assert px.min() >= 0 and px.max() <= 1
     assert np.abs(px.numpy() - gp["pixels"]).max() < 2e-5
 

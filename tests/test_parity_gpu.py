@@ -286,7 +286,8 @@ def test_full_batch64_tokens_bit_exact_against_oracle(full_engine):
 
 class _OracleVAE:
     """Stand-in for diffusers.AutoencoderKL with the reference's call shapes (SelftokPipeline.py:215,288,316): the SD3 VAE
-    arithmetic comes from oracle/vae_oracle.py (the checker; fp32 on the host) -- it is the VAE here, not the path."""
+    arithmetic comes from oracle/vae_oracle.py (the checker; fp32 on the host) -- it is the VAE here, not the path.
+    `decoder` (a capi.VaeDecoder) switches decode() to the device VAE of this repo; encode() stays on the oracle arithmetic."""
 
     class _Dist:
         def __init__(self, m):
@@ -295,8 +296,8 @@ class _OracleVAE:
         def mode(self):
             return self._m
 
-    def __init__(self, sd, ch_mult=(1, 2, 4, 4)):
-        self.sd, self.ch_mult = sd, ch_mult
+    def __init__(self, sd, ch_mult=(1, 2, 4, 4), decoder=None):
+        self.sd, self.ch_mult, self.decoder = sd, ch_mult, decoder
 
     def encode(self, x, return_dict=False):
         import vae_oracle as V
@@ -304,6 +305,8 @@ class _OracleVAE:
 
     def decode(self, z, return_dict=False):
         import vae_oracle as V
+        if self.decoder is not None:
+            return (self.decoder.decode(z),)
         return (V.decode(self.sd, z.float().cpu()).to(z.device),)
 
 
@@ -324,21 +327,24 @@ def _pixel_gate(px, px_ref, gt, what):
 
 def test_tiny_pixel_gate_through_pipeline_api(tiny_sd, gold):
     """encoding() / decoding() of the drop-in class with a VAE object of the reference's shape (the in-tree SDVAE arithmetic,
-    ch = 32): pixels of the 50-step decode against the reference's own pixels (tests/golden/tiny_pixels.npz)."""
+    full size): pixels of the 50-step decode against the reference's own pixels (tests/golden/tiny_pixels.npz) -- once with the
+    VAE arithmetic on the host (oracle) and once with this repo's DEVICE VAE decoder (f1)."""
     import vae_oracle as V
     from selftoktokenizer_b200 import SelftokPipeline
+    from selftoktokenizer_b200.capi import VaeDecoder
     g, gp = gold("tiny"), gold("tiny_pixels")
     d = C.TINY
-    vsd = synth.synth_vae_state_dict(ch=32)
-    for precision in ("fp16", "bf16x3"):
+    vsd = synth.synth_vae_state_dict(ch=128)
+    dev_vae = VaeDecoder(vsd, device=DEV)
+    for precision, vae in (("fp16", _OracleVAE(vsd)), ("bf16x3", _OracleVAE(vsd)), ("fp16", _OracleVAE(vsd, decoder=dev_vae))):
         pipe = SelftokPipeline(cfg=None, ckpt_path=None, sd3_path=None, datasize=d.latent * 8, dtype=torch.float32, device=DEV,
-                               state_dict=tiny_sd, dims=d, vae=_OracleVAE(vsd), precision=precision)
+                               state_dict=tiny_sd, dims=d, vae=vae, precision=precision)
         torch.manual_seed(1234)                                       # the reference's noise draw (CPU global generator)
         rec = pipe.decoding(g["tokens"], DEV)
         assert rec.dtype == torch.float32 and tuple(rec.shape) == (3, 3, 64, 64)
         x0 = synth.synth_tensor("golden.tiny.x0", (3, d.in_channels, d.latent, d.latent), "emb", 1.0)
         gt = V.images_from_latents(vsd, x0).numpy()
-        _pixel_gate(rec.cpu().numpy(), gp["pixels"], gt, f"tiny decoding() {precision}")
+        _pixel_gate(rec.cpu().numpy(), gp["pixels"], gt, f"tiny decoding() {precision}" + (" + device VAE" if vae.decoder else ""))
         # encoding(): images -> VAE -> process_in -> tokens; against the oracle run on the same VAE latents
         img = synth.synth_tensor("tiny.images", (2, 3, 64, 64), "emb", 0.5)
         tok = pipe.encoding(img, DEV)
@@ -346,6 +352,7 @@ def test_tiny_pixel_gate_through_pipeline_api(tiny_sd, gold):
         _, tok_ref, z_ref = O.encode(tiny_sd, d, lat)
         _check_tokens(tok.cpu().numpy(), tok_ref.numpy(), _top2_margin(tiny_sd, z_ref), f"tiny encoding() {precision}")
         pipe.engine.close()
+    dev_vae.close()
 
 
 def test_full_pixel_gate(full_engine, gold):
@@ -565,3 +572,44 @@ def test_guided_sampler_cfg(tiny_engine, gold):
     # scale 1 collapses to the conditional branch alone -- which is NOT decode(): the guided call site drops context_see_xt
     x1 = tiny_engine.decode_cfg(tok, noise, 1.0, steps=3)
     assert torch.isfinite(x1).all()
+
+
+@pytest.mark.parametrize("h,B", [(8, 3), (16, 2), (32, 2)])
+def test_device_vae_decoder_against_oracle(h, B):
+    """f1: the SD3 VAE decoder on the device (implicit-GEMM 3x3 convolutions on the tcgen05 kernel, GroupNorm + SiLU, the
+    single-head attention of the middle block) against the pinned restatement of the reference's SDVAE, seeded weights."""
+    import vae_oracle as V
+    from selftoktokenizer_b200.capi import VaeDecoder
+    vsd = synth.synth_vae_state_dict(ch=128, encoder=False)
+    z = synth.synth_tensor(f"vae.dev.z{h}", (B, 16, h, h), "emb", 1.0)
+    dec = VaeDecoder(vsd, device=DEV)
+    out = dec.decode(z).cpu()
+    out2 = dec.decode(z).cpu()
+    with torch.no_grad():
+        ref = V.decode(vsd, z)
+    err = float((out - ref).abs().max())
+    print(f"device VAE decode latent {h}x{h} B={B}: max-abs err {err:.3e} (|x|max {float(ref.abs().max()):.2f})")
+    assert torch.equal(out, out2), "the device VAE must be bit-reproducible"
+    assert err < 2e-4
+    n = dec.decode(z, norm_ip=True).cpu()
+    assert float(n.min()) >= 0.0 and float(n.max()) <= 1.0
+    assert float((n - (ref.clamp(-1, 1) + 1) / 2).abs().max()) < 1e-4
+    dec.close()
+
+
+def test_full_pixel_gate_on_device_vae(full_engine, gold):
+    """The pixel-boundary parity gate with EVERYTHING after the tokens on the device: 50-step decode (B = 1, full geometry) ->
+    process_out -> device VAE decoder -> norm_ip, against the reference's own pixels (tests/golden/full_pixels.npz)."""
+    import vae_oracle as V
+    from selftoktokenizer_b200.capi import VaeDecoder
+    g, ge, gp = gold("full_decode"), gold("full_encode"), gold("full_pixels")
+    d = C.FULL
+    vsd = synth.synth_vae_state_dict(ch=128, encoder=False)
+    dec = VaeDecoder(vsd, device=DEV)
+    x = full_engine.decode(torch.from_numpy(ge["tokens"][:1]), torch.from_numpy(g["noise"]))
+    px = dec.decode(x / V.SCALE + V.SHIFT, norm_ip=True).cpu().numpy()
+    with torch.no_grad():
+        x0 = synth.synth_tensor("golden.full.x0", (2, d.in_channels, d.latent, d.latent), "emb", 1.0)[:1]
+        gt = V.images_from_latents(vsd, x0).numpy()
+    _pixel_gate(px, gp["pixels"], gt, f"full decode {full_engine.precision} + device VAE")
+    dec.close()
