@@ -309,8 +309,11 @@ def run_gpu(args):
     eng = Engine(d, sd, device=dev, precision=args.precision, steps=DECODE_STEPS)
     del sd
     torch.cuda.empty_cache()
-    x0 = synth.synth_tensor(f"bench.x0.{rank}", (B, d.in_channels, d.latent, d.latent), "emb", 1.0, device=dev)
-    noise = synth.synth_tensor(f"bench.noise.{rank}", (B, d.in_channels, d.latent, d.latent), "emb", 1.0, device=dev)
+    # ONE global draw (index-hashed, so every rank evaluates the same tensor) sliced by rank: a sharded run works on exactly
+    # the latents / noise a single process would see for the global batch (SURVEY 8e RNG-parity rule)
+    lo, hi = rank * B, (rank + 1) * B
+    x0 = synth.synth_tensor("bench.x0.0", (B * world, d.in_channels, d.latent, d.latent), "emb", 1.0, device=dev)[lo:hi].contiguous()
+    noise = synth.synth_tensor("bench.noise.0", (B * world, d.in_channels, d.latent, d.latent), "emb", 1.0, device=dev)[lo:hi].contiguous()
     x0_h, noise_h = x0.cpu().pin_memory(), noise.cpu().pin_memory()
     tok_h = torch.empty(B, d.K, dtype=torch.int64).pin_memory()
     out_h = torch.empty_like(noise_h).pin_memory()

@@ -41,6 +41,8 @@ struct DecodeWs {       // activation workspace of the MMDiT for one batch size
   float *outs_q = nullptr, *x_lat = nullptr, *patch = nullptr, *ctx0 = nullptr, *ctx = nullptr, *x = nullptr;
   float *qkv = nullptr, *o_final = nullptr;      // qkv: fp32 joint buffer (fp32 mode only)
   float* o_final_u = nullptr;                    // final-layer output of the unconditional branch (guided sampler)
+  // split-bf16 operand planes of the two skinny fp32-faithful GEMMs of every evaluation (patch embedding K = 64, final layer N = 64)
+  bf16 *patch_hi = nullptr, *patch_lo = nullptr, *fin_hi = nullptr, *fin_lo = nullptr;
   bf16 *qkv_hi = nullptr, *qkv_lo = nullptr;     // joint q/k/v as 16-bit planes [B,S,3,H,64] (tensor-core modes)
   // fp32 mode activations
   float *a_c = nullptr, *a_x = nullptr, *attn_c = nullptr, *attn_x = nullptr, *h_c = nullptr, *h_x = nullptr;
@@ -432,6 +434,19 @@ extern "C" __attribute__((visibility("default"))) int selftok_finalize(selftok_h
           packed_names.push_back(name);
         }
   }
+  if (tc_mode(e)) {
+    // the patch embedding (K = 64) and the final layer (N = 64) stay fp32-faithful in every tensor-core mode: split-bf16 planes
+    // (hi + lo, three MMAs per product); their fp32 copies are kept (the fp32 FFMA mode and the table MLPs read them)
+    for (const char* nm : {"model.x_embedder.proj.weight", "model.final_layer.linear.weight"}) {
+      if (c.renderer && std::string(nm) == "model.x_embedder.proj.weight") continue;      // the renderer has no x_embedder
+      GETW(W, nm);
+      WPack p;
+      STK_TRY(dalloc(e, e->allocs, &p.hi, W->numel));
+      STK_TRY(dalloc(e, e->allocs, &p.lo, W->numel));
+      PROF(PC_OTHER, launch_split_bf16(W->d, p.hi, p.lo, W->numel, s, 0));
+      e->wp[nm] = p;
+    }
+  }
   STK_CUDA(cudaStreamSynchronize(s));
   for (void* p : scratch) cudaFree(p);
   // the fp32 staging copies of the packed MMDiT weights are not read again (their shapes are): release 8.3 GB
@@ -802,6 +817,10 @@ static int ensure_dws(selftok_engine* e, int B) {
     STK_TRY(dalloc(e, P, &w.h_x, B * N * 4 * D));
   } else {
     const bool lo = nsplit(e) == 3;
+    STK_TRY(dalloc(e, P, &w.patch_hi, B * N * c.in_channels * c.dit_patch * c.dit_patch));
+    STK_TRY(dalloc(e, P, &w.patch_lo, B * N * c.in_channels * c.dit_patch * c.dit_patch));
+    STK_TRY(dalloc(e, P, &w.fin_hi, B * N * D));
+    STK_TRY(dalloc(e, P, &w.fin_lo, B * N * D));
     STK_TRY(dalloc(e, P, &w.qkv_hi, B * S * 3 * D));
     if (lo) STK_TRY(dalloc(e, P, &w.qkv_lo, B * S * 3 * D));
     STK_TRY(dalloc(e, P, &w.a_c_hi, B * K * D));
@@ -864,6 +883,47 @@ static int post_attention(selftok_engine* e, const std::string& blk, float* resi
   STK_TRY(lintc(e, blk + "mlp.fc1", a_hi, a_lo, M, eh, s));
   er.gate = mod + 5 * D;
   return lintc(e, blk + "mlp.fc2", h_hi, h_lo, M, er, s);
+}
+
+// x = x_embedder(patches) + cropped pos_embed (mmdit.py:1000-1001) from ws.patch into ws.x.  Tensor-core modes: the K = 64 GEMM on
+// the tcgen05 kernel with split-bf16 operands (fp32-faithful) instead of the fp32 FFMA kernel (0.3 ms -> ~20 us per evaluation).
+static int x_embed(selftok_engine* e, int B, cudaStream_t s) {
+  const selftok_config_t& c = e->cfg;
+  DecodeWs& w = e->dws;
+  const int D = e->D, N = e->Nimg, Kp = c.in_channels * c.dit_patch * c.dit_patch;
+  Epilogue ep;
+  ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
+  if (!tc_mode(e) || Kp % 8 != 0) return lin32(e, "model.x_embedder.proj", w.patch, Kp, (int64_t)B * N, ep, s);
+  PROF(PC_OTHER, launch_split_bf16(w.patch, w.patch_hi, w.patch_lo, (int64_t)B * N * Kp, s, 0));
+  GETW(Bv, "model.x_embedder.proj.bias");
+  auto it = e->wp.find("model.x_embedder.proj.weight");
+  STK_CHECK(it != e->wp.end(), SELFTOK_ERR_STATE, "packed x_embedder missing");
+  ep.bias = Bv->d; ep.ldo = D;
+  PROF(PC_GEMM_TC, launch_gemm_tc(w.patch_hi, w.patch_lo, it->second.hi, it->second.lo, (int64_t)B * N, D, Kp, 3, ep, s, 0));
+  return 0;
+}
+// FinalLayer (mmdit.py:641-645): LN + modulate, then the N = p*p*C = 64 column linear -> o_out [B*N, 64] fp32
+static int final_layer(selftok_engine* e, int B, const float* fm, float* o_out, cudaStream_t s) {
+  DecodeWs& w = e->dws;
+  const int D = e->D;
+  const int64_t Mx = (int64_t)B * e->Nimg;
+  if (!tc_mode(e)) {
+    PROF(PC_LN, launch_ln_mod(w.x, D, fm, fm + D, 2 * D, 1, w.a_x, nullptr, nullptr, D, Mx, D, 1e-6f, s));
+    Epilogue ep;
+    ep.out = o_out;
+    return lin32(e, "model.final_layer.linear", w.a_x, D, Mx, ep, s);
+  }
+  LnProblem lp;
+  lp.x = w.x; lp.shift = fm; lp.scale = fm + D; lp.ld_mod = 2 * D; lp.period = 1; lp.out_hi = w.fin_hi; lp.out_lo = w.fin_lo; lp.M = Mx;
+  PROF(PC_LN, launch_ln_mod_pair(&lp, 1, D, 1e-6f, s, 0));
+  GETW(W, "model.final_layer.linear.weight");
+  GETW(Bv, "model.final_layer.linear.bias");
+  auto it = e->wp.find("model.final_layer.linear.weight");
+  STK_CHECK(it != e->wp.end(), SELFTOK_ERR_STATE, "packed final layer missing");
+  Epilogue ep;
+  ep.out = o_out; ep.bias = Bv->d; ep.ldo = (int)W->shape[0];
+  PROF(PC_GEMM_TC, launch_gemm_tc(w.fin_hi, w.fin_lo, it->second.hi, it->second.lo, Mx, (int)W->shape[0], D, 3, ep, s, 0));
+  return 0;
 }
 
 // forward_core_with_concat (mmdit.py:918-933) on the residual streams already initialised in ws.ctx / ws.x.
@@ -968,12 +1028,8 @@ static int joint_blocks(selftok_engine* e, int B, int Kc, int step, bool ctx_sel
     STK_TRY(post_attention(e, px, w.x, Mx, xmod, 6 * D, 1, w.attn_x, w.attn_x_hi, w.attn_x_lo, w.a_x, w.a_x_hi, w.a_x_lo,
                            w.h_x, w.h_x_hi, w.h_x_lo, s));
   }
-  // FinalLayer (mmdit.py:641-645): fp32 FFMA (N = p*p*C = 64 columns)
   const float* fm = (uncond ? e->final_mod_u : e->final_mod) + (int64_t)step * 2 * D;
-  PROF(PC_LN, launch_ln_mod(w.x, D, fm, fm + D, 2 * D, 1, w.a_x, nullptr, nullptr, D, Mx, D, 1e-6f, s));
-  Epilogue ep;
-  ep.out = o_out ? o_out : w.o_final;
-  return lin32(e, "model.final_layer.linear", w.a_x, D, Mx, ep, s);
+  return final_layer(e, B, fm, o_out ? o_out : w.o_final, s);
 }
 
 // context_embedder(outs_q) + context_pos_embed (mmdit.py:1026) — step invariant, computed once per call
@@ -990,11 +1046,9 @@ static int context_embed(selftok_engine* e, int B, cudaStream_t s) {
 static int dit_forward(selftok_engine* e, int B, int step, cudaStream_t s) {
   const selftok_config_t& c = e->cfg;
   DecodeWs& w = e->dws;
-  const int D = e->D, N = e->Nimg, Kc = e->k[step] + 1;
+  const int D = e->D, Kc = e->k[step] + 1;
   PROF(PC_OTHER, launch_patchify(w.x_lat, w.patch, B, c.in_channels, c.latent, c.latent, c.dit_patch, s));
-  Epilogue ep;
-  ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
-  STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
+  STK_TRY(x_embed(e, B, s));
   PROF(PC_OTHER, launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
   // context rows see the image keys unless the handle was created with context_see_xt = 0 (sd3/mmdit.py:1012,1060; the
   // reference pipeline's sampler passes context_see_xt=True, SelftokPipeline.py:259)
@@ -1008,15 +1062,13 @@ static int dit_forward(selftok_engine* e, int B, int step, cudaStream_t s) {
 static int dit_forward_cfg(selftok_engine* e, int B, int step, cudaStream_t s) {
   const selftok_config_t& c = e->cfg;
   DecodeWs& w = e->dws;
-  const int D = e->D, N = e->Nimg, Kc = e->k[step] + 1;
+  const int D = e->D, Kc = e->k[step] + 1;
   STK_CHECK(e->has_cfg, SELFTOK_ERR_STATE, "guided sampling needs selftok_set_cfg_schedule before selftok_finalize");
   PROF(PC_OTHER, launch_patchify(w.x_lat, w.patch, B, c.in_channels, c.latent, c.latent, c.dit_patch, s));
-  Epilogue ep;
-  ep.out = w.x; ep.addtab = e->dit_pos; ep.add_ld = D; ep.add_period = N;
-  STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
+  STK_TRY(x_embed(e, B, s));
   PROF(PC_OTHER, launch_copy_rows(w.ctx0, (int64_t)c.K * D, w.ctx, (int64_t)Kc * D, B, (int64_t)Kc * D, s));
   STK_TRY(joint_blocks(e, B, Kc, step, /*ctx_self=*/true, s, /*uncond=*/false, w.o_final));
-  STK_TRY(lin32(e, "model.x_embedder.proj", w.patch, c.in_channels * c.dit_patch * c.dit_patch, (int64_t)B * N, ep, s));
+  STK_TRY(x_embed(e, B, s));
   return joint_blocks(e, B, 0, step, /*ctx_self=*/false, s, /*uncond=*/true, w.o_final_u);
 }
 

@@ -32,3 +32,36 @@ def gather_tokens(local_tokens: torch.Tensor, n_total: int) -> torch.Tensor:
         lo, hi = shard_slice(n_total, r, world)
         rows.append(out[r * per: r * per + (hi - lo)])
     return torch.cat(rows, dim=0)
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) of the default process group; (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def host_noise(n_total: int, shape, seed: int) -> torch.Tensor:
+    """The sampler's initial noise for the WHOLE batch, drawn once on the host exactly as the reference draws it
+    (torch.randn on a CPU generator, SelftokPipeline.py:262-264) -- every rank evaluates the same deterministic draw and keeps
+    its slice, so a sharded run starts from the noise a single process would have used (SURVEY 8e RNG-parity rule)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return torch.randn(n_total, *shape, generator=g)
+
+
+def gather_rows(local: torch.Tensor, n_total: int) -> torch.Tensor:
+    """all-gather of ragged per-rank row blocks of any trailing shape / dtype (latents, pixels) into [n_total, ...]."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    w = dist.get_world_size()
+    per = (n_total + w - 1) // w
+    pad = torch.zeros(per, *local.shape[1:], dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty(w * per, *local.shape[1:], dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    rows = []
+    for r in range(w):
+        lo, hi = shard_slice(n_total, r, w)
+        rows.append(out[r * per: r * per + (hi - lo)])
+    return torch.cat(rows, dim=0)

@@ -240,6 +240,33 @@ class SelftokPipeline:
         self._raise_on_bad_ids(token_idx)
         return out
 
+    # ------------------------------------------------------------------ data-parallel entry points (one process per GPU)
+    @torch.no_grad()
+    def encode_latents_sharded(self, x_0_global: torch.Tensor) -> torch.Tensor:
+        """Every rank passes the SAME global batch (host tensor); each encodes its contiguous slice (dist.shard_slice) and the
+        token ids are all-gathered (NCCL over NVLink: [B/G, K] int64 per rank -- the path's only collective).
+        Returns the global [B, K] ids on every rank; identical, bit for bit, to a single-process encode."""
+        from . import dist as D
+        rank, world = D.world()
+        lo, hi = D.shard_slice(x_0_global.shape[0], rank, world)
+        return D.gather_tokens(self.engine.encode(x_0_global[lo:hi]), x_0_global.shape[0])
+
+    @torch.no_grad()
+    def decode_latents_sharded(self, idx_global, noise_global: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                               gather: bool = True) -> torch.Tensor:
+        """Global tokens [B, K] on every rank -> this rank's slice decoded; `gather` returns the global latents on every rank.
+        The initial noise is ONE host draw for the whole batch (dist.host_noise(seed)), sliced per rank."""
+        from . import dist as D
+        token_idx = torch.from_numpy(idx_global) if isinstance(idx_global, np.ndarray) else idx_global
+        n = token_idx.shape[0]
+        rank, world = D.world()
+        lo, hi = D.shard_slice(n, rank, world)
+        if noise_global is None:
+            latent_dim = self.datasize // 8
+            noise_global = D.host_noise(n, (self.dims.in_channels, latent_dim, latent_dim), 0 if seed is None else seed)
+        out = self.engine.decode(token_idx[lo:hi], noise_global[lo:hi])
+        return D.gather_rows(out, n) if gather else out
+
     # ------------------------------------------------------------------ reference API (pixel space, needs the SD3 VAE)
     def _need_vae(self):
         if self.vae is None:

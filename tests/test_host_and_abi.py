@@ -118,3 +118,33 @@ def test_token_gather_gloo_world2(tmp_path):
     for p in procs:
         out, err = p.communicate(timeout=120)
         assert p.returncode == 0 and "ok" in out, err
+
+
+_WORKER2 = """
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from selftoktokenizer_b200.dist import shard_slice, gather_rows, host_noise, world
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank, w = world()
+n = 5
+noise = host_noise(n, (4, 3, 3), seed=11)                       # the same draw on every rank
+lo, hi = shard_slice(n, rank, w)
+mine = noise[lo:hi] * 2.0                                         # stands for this rank's decode of its slice
+full = gather_rows(mine, n)
+assert torch.equal(full, noise * 2.0), rank
+g = torch.Generator(device="cpu"); g.manual_seed(11)
+assert torch.equal(noise, torch.randn(n, 4, 3, 3, generator=g))   # exactly the single-process draw
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_sharded_noise_and_row_gather_gloo_world2(tmp_path):
+    script = tmp_path / "w2.py"
+    script.write_text(_WORKER2)
+    port = str(31500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), REPO, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+             for r in range(2)]
+    for p in procs:
+        out, err = p.communicate(timeout=120)
+        assert p.returncode == 0 and "ok" in out, err
