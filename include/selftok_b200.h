@@ -168,6 +168,13 @@ int selftok_vae_finalize(selftok_vae_t v, void* stream);
 int selftok_vae_decode(selftok_vae_t v, const float* z_dev, int B, int h, int w, float* out_dev, int norm_ip, void* stream);
 int64_t selftok_vae_device_bytes(selftok_vae_t v);
 
+/* ---- activation workspace.  By default the library allocates ONE device block per operation class (0 = encode,
+ * 1 = decode / render / velocity) with cudaMalloc at the first call of a batch size.  A caller that owns device memory
+ * (PyTorch's caching allocator) can size it with selftok_workspace_bytes and hand it over with selftok_set_workspace; the
+ * library then allocates nothing at call time. */
+int64_t selftok_workspace_bytes(selftok_handle_t h, int B, int op);
+int selftok_set_workspace(selftok_handle_t h, int op, void* ws_dev, size_t bytes);
+
 /* ---- introspection ----------------------------------------------------------------------------------------- */
 /* Number of kernel launches issued (or replayed from a graph) by the last hot-path call on this handle. */
 int64_t selftok_last_launch_count(selftok_handle_t h);

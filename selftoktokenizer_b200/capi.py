@@ -24,7 +24,7 @@ SYMBOLS = [
     "selftok_create", "selftok_destroy", "selftok_last_error", "selftok_version", "selftok_load_tensor",
     "selftok_set_schedule", "selftok_finalize", "selftok_export_packed", "selftok_import_packed", "selftok_encode", "selftok_vq_argmax", "selftok_lookup",
     "selftok_set_cfg_schedule", "selftok_decode", "selftok_decode_cfg", "selftok_dit_velocity", "selftok_render", "selftok_encode_host", "selftok_decode_host",
-    "selftok_render_host", "selftok_id_errors", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
+    "selftok_render_host", "selftok_id_errors", "selftok_workspace_bytes", "selftok_set_workspace", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
     "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_set_gemm_ctas", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
     "selftok_k_attention_tc",
     "selftok_vae_create", "selftok_vae_destroy", "selftok_vae_load_tensor", "selftok_vae_finalize", "selftok_vae_decode", "selftok_vae_device_bytes",
@@ -78,6 +78,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.selftok_render_host.argtypes = [vp, vp, i32, vp, vp]
     lib.selftok_id_errors.argtypes = [vp, vp]
     lib.selftok_id_errors.restype = i64
+    lib.selftok_workspace_bytes.argtypes = [vp, i32, i32]
+    lib.selftok_workspace_bytes.restype = i64
+    lib.selftok_set_workspace.argtypes = [vp, i32, vp, C.c_size_t]
     lib.selftok_last_launch_count.argtypes = [vp]
     lib.selftok_last_launch_count.restype = i64
     lib.selftok_device_bytes.argtypes = [vp]
@@ -388,6 +391,23 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ misc
+    def workspace_bytes(self, B: int, op: str) -> int:
+        n = int(self.lib.selftok_workspace_bytes(self.h, B, {"encode": 0, "decode": 1}[op]))
+        if n < 0:
+            raise SelftokError("selftok_workspace_bytes failed")
+        return n
+
+    def use_torch_workspace(self, B: int) -> None:
+        """Allocate the activation workspaces for batches up to B from PyTorch's caching allocator and hand them to the library
+        (selftok_set_workspace): after this the hot path performs no cudaMalloc of its own."""
+        self._ws = {}
+        with torch.cuda.device(self.device):
+            for op, code in (("encode", 0), ("decode", 1)):
+                buf = torch.empty(self.workspace_bytes(B, op) + 256, dtype=torch.uint8, device=self.device)
+                off = (-buf.data_ptr()) % 256
+                self._ws[op] = buf
+                check(self.lib.selftok_set_workspace(self.h, code, buf.data_ptr() + off, buf.numel() - 256))
+
     def set_use_graph(self, enable: bool) -> None:
         check(self.lib.selftok_set_use_graph(self.h, int(enable)))
 

@@ -35,6 +35,24 @@ struct WPack {
   bf16* lo = nullptr;
 };
 
+// Bump allocator over ONE block of device memory: the activation workspaces are carved from it.  The block is either the
+// caller's (selftok_set_workspace: PyTorch keeps ownership, nothing is allocated behind its caching allocator) or one
+// cudaMalloc of exactly selftok_workspace_bytes.  dry = sizing pass only.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  bool dry = false;
+  template <typename T> int take(T** p, int64_t n) {
+    const size_t bytes = (sizeof(T) * (size_t)(n > 0 ? n : 1) + 255) & ~(size_t)255;
+    if (!dry) {
+      if (off + bytes > cap) { set_error("workspace too small"); return SELFTOK_ERR_BAD_ARG; }
+      *p = reinterpret_cast<T*>(base + off);
+    }
+    off += bytes;
+    return 0;
+  }
+};
+
 struct DecodeWs {       // activation workspace of the MMDiT for one batch size
   int B = 0;
   int64_t* tokens = nullptr;
@@ -50,14 +68,16 @@ struct DecodeWs {       // activation workspace of the MMDiT for one batch size
   bf16 *a_c_hi = nullptr, *a_c_lo = nullptr, *a_x_hi = nullptr, *a_x_lo = nullptr;
   bf16 *attn_c_hi = nullptr, *attn_c_lo = nullptr, *attn_x_hi = nullptr, *attn_x_lo = nullptr;
   bf16 *h_c_hi = nullptr, *h_c_lo = nullptr, *h_x_hi = nullptr, *h_x_lo = nullptr;
-  std::vector<void*> allocs;
+  void* own = nullptr;                           // the library's own block (NULL when the caller's workspace is in use)
+  size_t own_bytes = 0;
 };
 struct EncodeWs {
   int B = 0;
   float *x0 = nullptr, *patch = nullptr, *x = nullptr, *q = nullptr, *xn = nullptr, *qn = nullptr, *xqkv = nullptr,
         *xkv = nullptr, *qqkv = nullptr, *xattn = nullptr, *qattn = nullptr, *xh = nullptr, *qh = nullptr, *outs_q = nullptr;
   int64_t* tokens = nullptr;
-  std::vector<void*> allocs;
+  void* own = nullptr;
+  size_t own_bytes = 0;
 };
 
 struct selftok_engine {
@@ -84,6 +104,8 @@ struct selftok_engine {
   int* bad_ids = nullptr;               // device counter of out-of-range token ids seen by the lookup kernel
   DecodeWs dws;
   EncodeWs ews;
+  void* user_ws[2] = {nullptr, nullptr};          // caller-provided workspaces (selftok_set_workspace): [0] encode, [1] decode / render
+  size_t user_ws_bytes[2] = {0, 0};
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (B, steps) -> (exec, launches)
   int64_t last_launches = 0;
   // optional per-kernel-class timing (CUDA events around every launch; only meaningful with graphs disabled)
@@ -237,8 +259,14 @@ extern "C" __attribute__((visibility("default"))) int selftok_create(const selft
   return SELFTOK_OK;
 }
 
-static void free_dws(selftok_engine* e) { free_pool(e, e->dws.allocs); e->dws = DecodeWs(); }
-static void free_ews(selftok_engine* e) { free_pool(e, e->ews.allocs); e->ews = EncodeWs(); }
+static void free_dws(selftok_engine* e) {
+  if (e->dws.own) { cudaFree(e->dws.own); e->bytes -= (int64_t)e->dws.own_bytes; }
+  e->dws = DecodeWs();
+}
+static void free_ews(selftok_engine* e) {
+  if (e->ews.own) { cudaFree(e->ews.own); e->bytes -= (int64_t)e->ews.own_bytes; }
+  e->ews = EncodeWs();
+}
 
 extern "C" __attribute__((visibility("default"))) int selftok_destroy(selftok_handle_t e) {
   if (!e) return SELFTOK_OK;
@@ -627,30 +655,53 @@ extern "C" __attribute__((visibility("default"))) int selftok_import_packed(self
 }
 
 // ------------------------------------------------------------------------------------------------ encode
+static int layout_ews(selftok_engine* e, EncodeWs& w, int64_t B, Arena& A) {
+  const selftok_config_t& c = e->cfg;
+  const int64_t Ni = e->Nenc, K = c.K, Hh = c.enc_hidden, Q = c.enc_qdim;
+  STK_TRY(A.take(&w.x0, B * c.in_channels * c.latent * c.latent));
+  STK_TRY(A.take(&w.patch, B * Ni * c.in_channels * c.enc_patch * c.enc_patch));
+  STK_TRY(A.take(&w.x, B * Ni * Hh));
+  STK_TRY(A.take(&w.q, B * K * Q));
+  STK_TRY(A.take(&w.xn, B * Ni * Hh));
+  STK_TRY(A.take(&w.qn, B * K * Q));
+  STK_TRY(A.take(&w.xqkv, B * Ni * 3 * Hh));
+  STK_TRY(A.take(&w.xkv, B * Ni * 2 * Q));
+  STK_TRY(A.take(&w.qqkv, B * K * 3 * Q));
+  STK_TRY(A.take(&w.xattn, B * Ni * Hh));
+  STK_TRY(A.take(&w.qattn, B * K * Q));
+  STK_TRY(A.take(&w.xh, B * Ni * 4 * Hh));
+  STK_TRY(A.take(&w.qh, B * K * 4 * Q));
+  STK_TRY(A.take(&w.outs_q, B * K * c.code_dim));
+  STK_TRY(A.take(&w.tokens, B * K));
+  return 0;
+}
+// carve the workspace of `op` (0 encode, 1 decode / render) for batch B from the caller's block if it is large enough, else from
+// one cudaMalloc of exactly the needed size
+template <typename WS, typename LAYOUT>
+static int place_ws(selftok_engine* e, int op, WS& w, int B, LAYOUT layout) {
+  Arena dry;
+  dry.dry = true;
+  WS scratch;
+  STK_TRY(layout(scratch, (int64_t)B, dry));
+  Arena A;
+  if (e->user_ws[op] && e->user_ws_bytes[op] >= dry.off) {
+    A.base = reinterpret_cast<char*>(e->user_ws[op]);
+    A.cap = e->user_ws_bytes[op];
+  } else {
+    STK_CUDA(cudaMalloc(&w.own, dry.off));
+    w.own_bytes = dry.off;
+    e->bytes += (int64_t)dry.off;
+    A.base = reinterpret_cast<char*>(w.own);
+    A.cap = dry.off;
+  }
+  STK_TRY(layout(w, (int64_t)B, A));
+  w.B = B;
+  return 0;
+}
 static int ensure_ews(selftok_engine* e, int B) {
   if (e->ews.B >= B) return 0;
   free_ews(e);
-  EncodeWs& w = e->ews;
-  const selftok_config_t& c = e->cfg;
-  const int64_t Ni = e->Nenc, K = c.K, Hh = c.enc_hidden, Q = c.enc_qdim;
-  auto& P = w.allocs;
-  STK_TRY(dalloc(e, P, &w.x0, (int64_t)B * c.in_channels * c.latent * c.latent));
-  STK_TRY(dalloc(e, P, &w.patch, B * Ni * c.in_channels * c.enc_patch * c.enc_patch));
-  STK_TRY(dalloc(e, P, &w.x, B * Ni * Hh));
-  STK_TRY(dalloc(e, P, &w.q, B * K * Q));
-  STK_TRY(dalloc(e, P, &w.xn, B * Ni * Hh));
-  STK_TRY(dalloc(e, P, &w.qn, B * K * Q));
-  STK_TRY(dalloc(e, P, &w.xqkv, B * Ni * 3 * Hh));
-  STK_TRY(dalloc(e, P, &w.xkv, B * Ni * 2 * Q));
-  STK_TRY(dalloc(e, P, &w.qqkv, B * K * 3 * Q));
-  STK_TRY(dalloc(e, P, &w.xattn, B * Ni * Hh));
-  STK_TRY(dalloc(e, P, &w.qattn, B * K * Q));
-  STK_TRY(dalloc(e, P, &w.xh, B * Ni * 4 * Hh));
-  STK_TRY(dalloc(e, P, &w.qh, B * K * 4 * Q));
-  STK_TRY(dalloc(e, P, &w.outs_q, B * K * c.code_dim));
-  STK_TRY(dalloc(e, P, &w.tokens, B * K));
-  w.B = B;
-  return 0;
+  return place_ws(e, 0, e->ews, B, [&](EncodeWs& w, int64_t b, Arena& A) { return layout_ews(e, w, b, A); });
 }
 
 // Encoder.forward up to the quantizer input (models_ours.py:204-219,315-343; modules.py:310-327)
@@ -789,57 +840,57 @@ extern "C" __attribute__((visibility("default"))) int selftok_lookup(selftok_han
 }
 
 // ------------------------------------------------------------------------------------------------ decode
+static int layout_dws(selftok_engine* e, DecodeWs& w, int64_t B, Arena& A) {
+  const selftok_config_t& c = e->cfg;
+  const int64_t K = c.K, N = e->Nimg, D = e->D, S = K + N;
+  STK_TRY(A.take(&w.tokens, B * K));
+  STK_TRY(A.take(&w.outs_q, B * K * c.code_dim));
+  STK_TRY(A.take(&w.x_lat, B * c.in_channels * c.latent * c.latent));
+  STK_TRY(A.take(&w.patch, B * N * c.in_channels * c.dit_patch * c.dit_patch));
+  STK_TRY(A.take(&w.ctx0, B * K * D));
+  STK_TRY(A.take(&w.ctx, B * K * D));
+  STK_TRY(A.take(&w.x, B * N * D));
+  STK_TRY(A.take(&w.o_final, B * N * c.dit_patch * c.dit_patch * c.in_channels));
+  STK_TRY(A.take(&w.o_final_u, B * N * c.dit_patch * c.dit_patch * c.in_channels));
+  STK_TRY(A.take(&w.a_x, B * N * D));                       // fp32 LN output of the final layer (both modes)
+  if (!tc_mode(e)) {
+    STK_TRY(A.take(&w.qkv, B * S * 3 * D));
+    STK_TRY(A.take(&w.a_c, B * K * D));
+    STK_TRY(A.take(&w.attn_c, B * K * D));
+    STK_TRY(A.take(&w.attn_x, B * N * D));
+    STK_TRY(A.take(&w.h_c, B * K * 4 * D));
+    STK_TRY(A.take(&w.h_x, B * N * 4 * D));
+  } else {
+    const bool lo = nsplit(e) == 3;
+    STK_TRY(A.take(&w.patch_hi, B * N * c.in_channels * c.dit_patch * c.dit_patch));
+    STK_TRY(A.take(&w.patch_lo, B * N * c.in_channels * c.dit_patch * c.dit_patch));
+    STK_TRY(A.take(&w.fin_hi, B * N * D));
+    STK_TRY(A.take(&w.fin_lo, B * N * D));
+    STK_TRY(A.take(&w.qkv_hi, B * S * 3 * D));
+    if (lo) STK_TRY(A.take(&w.qkv_lo, B * S * 3 * D));
+    STK_TRY(A.take(&w.a_c_hi, B * K * D));
+    STK_TRY(A.take(&w.a_x_hi, B * N * D));
+    STK_TRY(A.take(&w.attn_c_hi, B * K * D));
+    STK_TRY(A.take(&w.attn_x_hi, B * N * D));
+    STK_TRY(A.take(&w.h_c_hi, B * K * 4 * D));
+    STK_TRY(A.take(&w.h_x_hi, B * N * 4 * D));
+    if (lo) {
+      STK_TRY(A.take(&w.a_c_lo, B * K * D));
+      STK_TRY(A.take(&w.a_x_lo, B * N * D));
+      STK_TRY(A.take(&w.attn_c_lo, B * K * D));
+      STK_TRY(A.take(&w.attn_x_lo, B * N * D));
+      STK_TRY(A.take(&w.h_c_lo, B * K * 4 * D));
+      STK_TRY(A.take(&w.h_x_lo, B * N * 4 * D));
+    }
+  }
+  return 0;
+}
 static int ensure_dws(selftok_engine* e, int B) {
   if (e->dws.B >= B) return 0;
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);   // graphs hold pointers into the old workspace
   e->graphs.clear();
   free_dws(e);
-  DecodeWs& w = e->dws;
-  const selftok_config_t& c = e->cfg;
-  const int64_t K = c.K, N = e->Nimg, D = e->D, S = K + N;
-  auto& P = w.allocs;
-  STK_TRY(dalloc(e, P, &w.tokens, B * K));
-  STK_TRY(dalloc(e, P, &w.outs_q, B * K * c.code_dim));
-  STK_TRY(dalloc(e, P, &w.x_lat, (int64_t)B * c.in_channels * c.latent * c.latent));
-  STK_TRY(dalloc(e, P, &w.patch, B * N * c.in_channels * c.dit_patch * c.dit_patch));
-  STK_TRY(dalloc(e, P, &w.ctx0, B * K * D));
-  STK_TRY(dalloc(e, P, &w.ctx, B * K * D));
-  STK_TRY(dalloc(e, P, &w.x, B * N * D));
-  STK_TRY(dalloc(e, P, &w.o_final, B * N * c.dit_patch * c.dit_patch * c.in_channels));
-  STK_TRY(dalloc(e, P, &w.o_final_u, B * N * c.dit_patch * c.dit_patch * c.in_channels));
-  STK_TRY(dalloc(e, P, &w.a_x, B * N * D));                       // fp32 LN output of the final layer (both modes)
-  if (!tc_mode(e)) {
-    STK_TRY(dalloc(e, P, &w.qkv, B * S * 3 * D));
-    STK_TRY(dalloc(e, P, &w.a_c, B * K * D));
-    STK_TRY(dalloc(e, P, &w.attn_c, B * K * D));
-    STK_TRY(dalloc(e, P, &w.attn_x, B * N * D));
-    STK_TRY(dalloc(e, P, &w.h_c, B * K * 4 * D));
-    STK_TRY(dalloc(e, P, &w.h_x, B * N * 4 * D));
-  } else {
-    const bool lo = nsplit(e) == 3;
-    STK_TRY(dalloc(e, P, &w.patch_hi, B * N * c.in_channels * c.dit_patch * c.dit_patch));
-    STK_TRY(dalloc(e, P, &w.patch_lo, B * N * c.in_channels * c.dit_patch * c.dit_patch));
-    STK_TRY(dalloc(e, P, &w.fin_hi, B * N * D));
-    STK_TRY(dalloc(e, P, &w.fin_lo, B * N * D));
-    STK_TRY(dalloc(e, P, &w.qkv_hi, B * S * 3 * D));
-    if (lo) STK_TRY(dalloc(e, P, &w.qkv_lo, B * S * 3 * D));
-    STK_TRY(dalloc(e, P, &w.a_c_hi, B * K * D));
-    STK_TRY(dalloc(e, P, &w.a_x_hi, B * N * D));
-    STK_TRY(dalloc(e, P, &w.attn_c_hi, B * K * D));
-    STK_TRY(dalloc(e, P, &w.attn_x_hi, B * N * D));
-    STK_TRY(dalloc(e, P, &w.h_c_hi, B * K * 4 * D));
-    STK_TRY(dalloc(e, P, &w.h_x_hi, B * N * 4 * D));
-    if (lo) {
-      STK_TRY(dalloc(e, P, &w.a_c_lo, B * K * D));
-      STK_TRY(dalloc(e, P, &w.a_x_lo, B * N * D));
-      STK_TRY(dalloc(e, P, &w.attn_c_lo, B * K * D));
-      STK_TRY(dalloc(e, P, &w.attn_x_lo, B * N * D));
-      STK_TRY(dalloc(e, P, &w.h_c_lo, B * K * 4 * D));
-      STK_TRY(dalloc(e, P, &w.h_x_lo, B * N * 4 * D));
-    }
-  }
-  w.B = B;
-  return 0;
+  return place_ws(e, 1, e->dws, B, [&](DecodeWs& w, int64_t b, Arena& A) { return layout_dws(e, w, b, A); });
 }
 
 // One stream of one JointBlock: LN+modulate -> qkv GEMM into the joint buffer   (mmdit.py:441-483, 521-529)
@@ -1089,6 +1140,34 @@ static int decode_body(selftok_engine* e, int B, int steps, cudaStream_t s, bool
     }
   }
   return 0;
+}
+
+// Bytes of activation workspace op (0: selftok_encode*, 1: selftok_decode* / selftok_render* / selftok_dit_velocity) needs for batch B.
+extern "C" __attribute__((visibility("default"))) int64_t selftok_workspace_bytes(selftok_handle_t e, int B, int op) {
+  if (!e || B <= 0 || (op != 0 && op != 1)) return -1;
+  Arena dry;
+  dry.dry = true;
+  if (op == 0) { EncodeWs w; if (layout_ews(e, w, B, dry) != 0) return -1; }
+  else { DecodeWs w; if (layout_dws(e, w, B, dry) != 0) return -1; }
+  return (int64_t)dry.off;
+}
+// Hand the library a caller-owned device block for workspace `op` (NULL / 0 returns to library-owned memory).  While it is at
+// least selftok_workspace_bytes(h, B, op) large, calls with batch <= B allocate nothing; the block must stay alive and must not
+// be used by anything else while a call on this handle is in flight.  Captured CUDA graphs of the decode loop are dropped.
+extern "C" __attribute__((visibility("default"))) int selftok_set_workspace(selftok_handle_t e, int op, void* ws_dev, size_t bytes) {
+  STK_CHECK(e && (op == 0 || op == 1), SELFTOK_ERR_BAD_ARG, "selftok_set_workspace: bad argument");
+  STK_CHECK((reinterpret_cast<uintptr_t>(ws_dev) & 255) == 0, SELFTOK_ERR_BAD_ARG, "selftok_set_workspace: the block must be 256-byte aligned");
+  STK_CUDA(cudaSetDevice(e->cfg.device));
+  STK_CUDA(cudaDeviceSynchronize());
+  e->user_ws[op] = bytes ? ws_dev : nullptr;
+  e->user_ws_bytes[op] = ws_dev ? bytes : 0;
+  if (op == 0) free_ews(e);
+  else {
+    for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);
+    e->graphs.clear();
+    free_dws(e);
+  }
+  return SELFTOK_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int selftok_set_use_graph(selftok_handle_t e, int enable) {

@@ -613,3 +613,24 @@ def test_full_pixel_gate_on_device_vae(full_engine, gold):
         gt = V.images_from_latents(vsd, x0).numpy()
     _pixel_gate(px, gp["pixels"], gt, f"full decode {full_engine.precision} + device VAE")
     dec.close()
+
+
+def test_caller_owned_workspace(tiny_engine, gold):
+    """the activation workspace can be the caller's (PyTorch-allocated) block, sized by selftok_workspace_bytes: results
+    are bit-identical and the library allocates nothing of its own for it."""
+    g = gold("tiny")
+    d = C.TINY
+    tok, noise = torch.from_numpy(g["tokens"]), torch.from_numpy(g["noise"])
+    x0 = synth.synth_tensor("golden.tiny.x0", (3, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    ref_t, ref_x = tiny_engine.encode(x0).cpu(), tiny_engine.decode(tok, noise).cpu()
+    own = tiny_engine.device_bytes
+    need = tiny_engine.workspace_bytes(3, "decode") + tiny_engine.workspace_bytes(3, "encode")
+    assert need > 0
+    tiny_engine.use_torch_workspace(3)
+    assert tiny_engine.device_bytes < own                             # the library's own blocks were released
+    base = tiny_engine.device_bytes
+    assert torch.equal(tiny_engine.encode(x0).cpu(), ref_t) and torch.equal(tiny_engine.decode(tok, noise).cpu(), ref_x)
+    assert tiny_engine.device_bytes == base                           # nothing allocated behind the caller's back
+    # a larger batch than the block was sized for falls back to a library-owned block, transparently
+    x5 = synth.synth_tensor("ws.x0", (5, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    assert tiny_engine.encode(x5).shape[0] == 5 and tiny_engine.device_bytes > base
