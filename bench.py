@@ -289,6 +289,18 @@ def run_extras(args, eng, dev, x0, noise, timed):
         er.close()
         del er
         torch.cuda.empty_cache()
+    # ---- f1: the SD3 VAE decoder on the device (what follows the token path in decoding()): latents -> pixels, batch 64
+    try:
+        from selftoktokenizer_b200.capi import VaeDecoder
+        dec = VaeDecoder(synth.synth_vae_state_dict(ch=128, encoder=False, device=dev), device=dev)
+        z = noise * 0.5
+        dec.decode(z)
+        msv, _ = timed(lambda: dec.decode(z, norm_ip=True) is None, 3)
+        out["vae_decode"] = {"workload": f"batch={B} SD3 VAE decoder, 32x32x16 latents -> 256x256 pixels (split-bf16 tcgen05 implicit-GEMM convs)",
+                             "value": B * 3 / (msv / 1000.0), "unit": UNIT, "ms_per_batch": msv / 3, "algorithmic_tflop_per_batch": 0.622 * B}
+        dec.close()
+    except Exception as exc:  # noqa: BLE001 - the headline must not die on an auxiliary record
+        out["vae_decode"] = {"error": str(exc)[:200]}
     return out
 
 

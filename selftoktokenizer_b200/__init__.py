@@ -11,7 +11,7 @@ __all__ = ["SelftokPipeline", "NormalizeToTensor", "parse_args_from_yaml", "Self
 
 
 def __getattr__(name):
-    if name in ("SelftokPipeline", "NormalizeToTensor", "norm_ip"):
+    if name in ("SelftokPipeline", "NormalizeToTensor", "norm_ip", "DeviceVAE"):
         from . import pipeline
         return getattr(pipeline, name)
     raise AttributeError(name)

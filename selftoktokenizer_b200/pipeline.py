@@ -62,16 +62,45 @@ class SD3LatentFormat:
         return (latent / self.scale_factor) + self.shift_factor
 
 
+class DeviceVAE:
+    """`self.vae` with the call shape the pipeline uses (SelftokPipeline.py:215,288,316): `decode` runs on this repo's device VAE
+    decoder (csrc/vae.cu, fp32-faithful split-bf16 GEMMs), `encode` is delegated to `encoder_vae` (e.g. the diffusers
+    AutoencoderKL) -- the VAE encoder is not on the device yet.  `decoder_state_dict`: SDVAE keys, or diffusers keys
+    (`diffusers_keys=True`)."""
+
+    def __init__(self, decoder_state_dict, device, encoder_vae=None, diffusers_keys: bool = False):
+        from .capi import VaeDecoder
+        sd = VaeDecoder.from_diffusers_keys(decoder_state_dict) if diffusers_keys else decoder_state_dict
+        self.decoder = VaeDecoder(sd, device=device)
+        self.encoder_vae = encoder_vae
+
+    def decode(self, z, return_dict=False):
+        out = self.decoder.decode(z).to(z.dtype)
+        return (out,)
+
+    def encode(self, x, return_dict=False):
+        if self.encoder_vae is None:
+            raise SelftokError("DeviceVAE: no encoder (pass encoder_vae=..., e.g. diffusers.AutoencoderKL)")
+        return self.encoder_vae.encode(x, return_dict=return_dict)
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+
 def _load_vae(sd3_path, device, dtype):
     try:
         from diffusers import AutoencoderKL  # noqa: WPS433 (optional, external weights)
     except Exception as exc:  # pragma: no cover - diffusers is not in the build image
-        raise SelftokError("the pixel-space API needs diffusers.AutoencoderKL (SD3 VAE); use the *_latents methods "
-                           "at the latent boundary instead") from exc
+        raise SelftokError("the pixel-space API needs diffusers.AutoencoderKL (SD3 VAE) for the encoder side, or pass vae=...; use "
+                           "the *_latents methods at the latent boundary instead") from exc
     vae = AutoencoderKL.from_pretrained(sd3_path, subfolder="vae")
     vae.to(device).to(dtype)
     vae.eval()
-    return vae
+    # decode on this repo's device VAE, encode on the diffusers module
+    return DeviceVAE(vae.state_dict(), device, encoder_vae=vae, diffusers_keys=True)
 
 
 def _decoder_state(state_dict: Dict, ema_decoder: bool) -> Dict[str, torch.Tensor]:
