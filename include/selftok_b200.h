@@ -27,7 +27,8 @@
  * never aborts); selftok_last_error() returns a thread-local description of the last failure.  Pointers named
  * *_dev are CUDA device pointers on the handle's device, *_host are host pointers.  All launches are ordered on
  * the `stream` argument (a cudaStream_t passed as void*; NULL = legacy default stream).  One handle per
- * device; a handle may be used by one host thread at a time.  The library allocates its weights, static
+ * device; a handle may be used by one host thread at a time and has ONE set of workspaces: at most one hot-path call per
+ * handle may be in flight (issue the next one on the same stream, or synchronise first).  The library allocates its weights, static
  * tables and activation workspace with cudaMalloc at finalize / first use of a batch size and frees them in
  * selftok_destroy; it never touches caller buffers other than the documented outputs.
  */

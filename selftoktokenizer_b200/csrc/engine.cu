@@ -1203,7 +1203,9 @@ static int decode_impl(selftok_handle_t e, const int64_t* tokens_dev, const floa
   const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
   if (tokens_dev != w.tokens) STK_CUDA(cudaMemcpyAsync(w.tokens, tokens_dev, sizeof(int64_t) * B * e->cfg.K, cudaMemcpyDeviceToDevice, s));
   if (noise_dev != w.x_lat) STK_CUDA(cudaMemcpyAsync(w.x_lat, noise_dev, sizeof(float) * nlat, cudaMemcpyDeviceToDevice, s));
-  if (!e->use_graph || guided) {          // the guided loop takes cfg_scale as a kernel argument: launched eagerly, not captured
+  // eager when asked to, for the guided loop (cfg_scale is a kernel argument) and whenever per-launch profiling is on (events
+  // recorded inside a capture never execute on a real stream: their elapsed times would be garbage)
+  if (!e->use_graph || guided || e->prof_on) {
     STK_TRY(decode_body(e, B, steps, s, guided, cfg_scale));
     e->last_launches = g_launch_count - launches0;
   } else {
@@ -1212,7 +1214,13 @@ static int decode_impl(selftok_handle_t e, const int64_t* tokens_dev, const floa
     if (it == e->graphs.end()) {
       cudaStream_t cs;
       STK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      STK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      {
+        const cudaError_t be = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (be != cudaSuccess) {
+          cudaStreamDestroy(cs);                                       // no leak on the error path
+          STK_CUDA(be);
+        }
+      }
       const int64_t l0 = g_launch_count;
       int st = decode_body(e, B, steps, cs);
       cudaGraph_t graph = nullptr;
