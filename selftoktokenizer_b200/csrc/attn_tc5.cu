@@ -46,6 +46,12 @@ constexpr int HD = 64, BQ = 128, BKV = 64;
 #define SELFTOK_ATTN5_NSB 2
 #endif
 constexpr int NSB = SELFTOK_ATTN5_NSB;
+// 1 = the Q K^T instructions are issued by the TMA thread (warp 0), warp 1 issues only P V: neither issuer waits behind the
+//     other one's blocking tcgen05.mma issue, and Q K^T of tile g + NSB is launched the moment P V of tile g retires
+#ifndef SELFTOK_ATTN5_SPLIT_ISSUE
+#define SELFTOK_ATTN5_SPLIT_ISSUE 0
+#endif
+constexpr bool SPLIT_ISSUE = SELFTOK_ATTN5_SPLIT_ISSUE != 0;
 constexpr int Q_BYTES = BQ * HD * 2, KV_TILE_BYTES = BKV * HD * 2;
 constexpr int XCH_BYTES = 6 * BQ * 4;               // row-max exchange (2 parities x 2 halves) + partial-sum exchange (2 halves)
 // NSPLIT == 1: single-pass 16-bit operands, 2 CTAs per SM.  NSPLIT == 3 ("bf16x3", fp32-faithful): every product is
@@ -85,6 +91,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {      // non-blocking
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
