@@ -9,7 +9,7 @@ sys.path.insert(0, REPO)
 from selftoktokenizer_b200 import capi  # noqa: E402
 ns = int(sys.argv[1])
 dev = torch.device("cuda:0")
-B, H = 16, 24
+B, H = int(os.environ.get("ATTN_CHECK_B", "16")), 24
 for S in [int(x) for x in sys.argv[2:]]:
     g = torch.Generator().manual_seed(S)
     qkv = torch.randn(B, S, 3, H, 64, generator=g).to(dev)

@@ -10,15 +10,15 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 C=$ROOT/selftoktokenizer_b200/csrc
 mkdir -p $ROOT/build/ab
 F="$EXTRA -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -I$C -diag-suppress 177"
-declare -A obj=( [kernels_simt]=$C/kernels_simt.o [gemm_tc]=$C/gemm_tc.o [attn_tc5]=$C/attn_tc5.o [engine]=$C/engine.o )
+declare -A obj=( [kernels_simt]=$C/kernels_simt.o [gemm_tc]=$C/gemm_tc.o [attn_tc5]=$C/attn_tc5.o [engine]=$C/engine.o [vae]=$C/vae.o )
 for src in "$@"; do
   b=$(basename $src .cu)
   role=""
-  for r in attn_tc5 kernels_simt gemm_tc engine; do case $b in $r*) role=$r; break;; esac; done
+  for r in attn_tc5 kernels_simt gemm_tc engine vae; do case $b in $r*) role=$r; break;; esac; done
   [ -n "$role" ] || { echo "cannot map $src to a source role"; exit 1; }
   nvcc $F -c $src -o $ROOT/build/ab/${b}_$name.o
   obj[$role]=$ROOT/build/ab/${b}_$name.o
 done
-nvcc -shared -o $ROOT/build/ab/lib_$name.so ${obj[kernels_simt]} ${obj[gemm_tc]} ${obj[attn_tc5]} ${obj[engine]} \
+nvcc -shared -o $ROOT/build/ab/lib_$name.so ${obj[kernels_simt]} ${obj[gemm_tc]} ${obj[attn_tc5]} ${obj[engine]} ${obj[vae]} \
   -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -cudart static
 echo built build/ab/lib_$name.so

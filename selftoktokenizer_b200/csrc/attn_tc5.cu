@@ -287,6 +287,46 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   // [32 half, 32 half + 16) -- nobody else reads those, and Q K^T of tile g+2 (same buffer) is issued after P V of tile g.
   const uint32_t s_tmem0 = tmem_base, o_tmem0 = tmem_base + 64 * NSB;
 
+  // The issuing threads walk the (item, tile) sequence with cursors: the Q K^T cursor runs ahead of the P V cursor (across
+  // item boundaries), so S_{g + NSB - 1} is being computed while the softmax warps work on S_g.
+  struct Cur { int item, n, j, nt; };
+  auto cur_first = [&]() {
+    Cur c{(int)blockIdx.x, 0, 0, 0};
+    c.nt = c.item < n_items ? item_tiles(c.item % nq) : 0;
+    return c;
+  };
+  auto cur_next = [&](Cur& c) {
+    if (++c.j == c.nt) {
+      c.item += gridDim.x; ++c.n; c.j = 0;
+      c.nt = c.item < n_items ? item_tiles(c.item % nq) : 0;
+    }
+  };
+  Cur cq = cur_first();
+  int gq = 0;
+  const uint32_t idesc_qk = make_idesc(BQ, BKV, FP16 ? 1 : 0, 0);              // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
+  // S[SB(gq)] = Q K_gq^T, then advance the cursor.  wait_free: the caller is not the P V issuer, so the buffer's previous
+  // occupant (tile gq - NSB) must be seen retired explicitly instead of through the issue order of one thread.
+  auto issue_qk = [&](bool wait_free) {
+    const int qb = cq.n & 1, st = gq % KV_STAGES;
+    if (cq.j == 0) mbar_wait(q_full(qb), (cq.n >> 1) & 1);
+    mbar_wait(kv_full(st), (gq / KV_STAGES) & 1);
+    if (wait_free && gq >= NSB) mbar_wait(pv_done(SB(gq)), SPH(gq - NSB));
+    tc_fence_after();
+    const uint32_t ks = kv_s + st * C::KV_STAGE, qs = q_s + qb * C::Q_STAGE;
+#pragma unroll
+    for (int k = 0; k < HD / 16; ++k) {                                  // K dimension = head dim: 32 B per k-step inside the row
+      tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
+      if (NSPLIT == 3) {                                                 // + Q_hi K_lo^T + Q_lo K_hi^T
+        tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + 2 * KV_TILE_BYTES + k * 32), idesc_qk, 1u);
+        tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + Q_BYTES + k * 32), make_smem_desc(ks + k * 32), idesc_qk, 1u);
+      }
+    }
+    tc_commit(s_full(SB(gq)));
+    if (cq.j == cq.nt - 1) tc_commit(q_empty(qb));                      // last tile of the item: Q buffer reusable
+    cur_next(cq);
+    ++gq;
+  };
+
   if (warp == 0) {
     // =========================================================== TMA producer
     if (lane == 0) {
@@ -298,9 +338,51 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         tma_load_2d(q_s + qb * C::Q_STAGE, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
         if (NSPLIT == 3) tma_load_2d(q_s + qb * C::Q_STAGE + Q_BYTES, &map_q_lo, q_full(qb), h * HD, b * S + qt * BQ);
       };
+      auto load_kv = [&](int item, int j, int g) {
+        const int h = (item / nq) % p.H, b = item / (nq * p.H);
+        const int row0 = b * S;                                           // first row of this image in the [B*S, 3*H*64] matrix
+        const int st = g % KV_STAGES;
+        mbar_wait(kv_empty(st), ((g / KV_STAGES) & 1) ^ 1);
+        const uint32_t ks = kv_s + st * C::KV_STAGE;
+        mbar_expect_tx(kv_full(st), C::KV_STAGE);
+        tma_load_2d(ks, &map_kv, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
+        tma_load_2d(ks + KV_TILE_BYTES, &map_kv, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+        if (NSPLIT == 3) {
+          tma_load_2d(ks + 2 * KV_TILE_BYTES, &map_kv_lo, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
+          tma_load_2d(ks + 3 * KV_TILE_BYTES, &map_kv_lo, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
+        }
+      };
+      if (SPLIT_ISSUE) {
+        // this thread also issues Q K^T, two tiles behind its own K/V loads (the loads stay a tile period ahead of their use).
+        // The next item's Q is fetched as soon as its buffer is seen free (non-blocking test), at the latest right before the
+        // Q K^T that needs it -- a blocking wait at the item start would wait for a Q K^T this thread has not issued yet.
+        Cur ct = cur_first();
+        int gt = 0, pend_item = -1, pend_n = 0;
+        if (ct.item < n_items) load_q(ct.item, 0);
+        while (cq.item < n_items) {
+          if (pend_item >= 0 && mbar_test(q_empty(pend_n & 1), ((pend_n >> 1) & 1) ^ 1)) { load_q(pend_item, pend_n); pend_item = -1; }
+          if (ct.item < n_items) {
+            if (ct.j == 0 && ct.item + (int)gridDim.x < n_items) {
+              while (pend_item >= 0) {                                    // short items: the previous prefetch is still owed
+                if (gq < gt && pend_n != cq.n) issue_qk(true);
+                else { load_q(pend_item, pend_n); pend_item = -1; }
+                if (pend_item >= 0 && mbar_test(q_empty(pend_n & 1), ((pend_n >> 1) & 1) ^ 1)) { load_q(pend_item, pend_n); pend_item = -1; }
+              }
+              pend_item = ct.item + gridDim.x; pend_n = ct.n + 1;
+            }
+            load_kv(ct.item, ct.j, gt);
+            cur_next(ct);
+            ++gt;
+          }
+          if (gq + 2 < gt || ct.item >= n_items) {
+            if (pend_item >= 0 && pend_n == cq.n) { load_q(pend_item, pend_n); pend_item = -1; }
+            issue_qk(true);
+          }
+        }
+      }
       int g = 0, n = 0;
-      if ((int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
+      if (!SPLIT_ISSUE && (int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
+      for (int item = blockIdx.x; !SPLIT_ISSUE && item < n_items; item += gridDim.x, ++n) {
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
         const int row0 = b * S;                                         // first row of this image in the [B*S, 3*H*64] matrix
         const int n_tiles = item_tiles(qt);
@@ -323,47 +405,12 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   } else if (warp == 1) {
     // =========================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_qk = make_idesc(BQ, BKV, FP16 ? 1 : 0, 0);          // S[128 x 64 keys]: B = K tile, K-major (d contiguous)
       const uint32_t idesc_pv = make_idesc(BQ, HD, FP16 ? 1 : 0, 1);           // O[128 x 64 dims]: B = V tile, MN-major (d contiguous)
-      // Two cursors walk the same (item, tile) sequence: the Q K^T cursor runs NSB - 1 tiles ahead of the P V cursor (across
-      // item boundaries), so S_{g + NSB - 1} is being computed while the softmax warps work on S_g.
-      struct Cur { int item, n, j, nt; };
-      auto cur_first = [&]() {
-        Cur c{(int)blockIdx.x, 0, 0, 0};
-        c.nt = c.item < n_items ? item_tiles(c.item % nq) : 0;
-        return c;
-      };
-      auto cur_next = [&](Cur& c) {
-        if (++c.j == c.nt) {
-          c.item += gridDim.x; ++c.n; c.j = 0;
-          c.nt = c.item < n_items ? item_tiles(c.item % nq) : 0;
-        }
-      };
-      Cur cq = cur_first();
-      int gq = 0;
-      auto issue_qk = [&]() {                                          // S[SB(gq)] = Q K_gq^T, then advance the cursor
-        const int qb = cq.n & 1, st = gq % KV_STAGES;
-        if (cq.j == 0) mbar_wait(q_full(qb), (cq.n >> 1) & 1);
-        mbar_wait(kv_full(st), (gq / KV_STAGES) & 1);
-        tc_fence_after();
-        const uint32_t ks = kv_s + st * C::KV_STAGE, qs = q_s + qb * C::Q_STAGE;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {                              // K dimension = head dim: 32 B per k-step inside the row
-          tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + k * 32), idesc_qk, k > 0 ? 1u : 0u);
-          if (NSPLIT == 3) {                                             // + Q_hi K_lo^T + Q_lo K_hi^T
-            tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + k * 32), make_smem_desc(ks + 2 * KV_TILE_BYTES + k * 32), idesc_qk, 1u);
-            tc_mma_f16(s_tmem0 + 64 * SB(gq), make_smem_desc(qs + Q_BYTES + k * 32), make_smem_desc(ks + k * 32), idesc_qk, 1u);
-          }
-        }
-        tc_commit(s_full(SB(gq)));
-        if (cq.j == cq.nt - 1) tc_commit(q_empty(qb));                  // last tile of the item: Q buffer reusable
-        cur_next(cq);
-        ++gq;
-      };
-      for (int i = 0; i < NSB - 1 && cq.item < n_items; ++i) issue_qk();
+      if (!SPLIT_ISSUE)
+        for (int i = 0; i < NSB - 1 && cq.item < n_items; ++i) issue_qk(false);
       Cur cp = cur_first();
       for (int g = 0; cp.item < n_items; ++g) {
-        if (cq.item < n_items) issue_qk();                               // look-ahead Q K^T (its S buffer was freed by P V_{g-1})
+        if (!SPLIT_ISSUE && cq.item < n_items) issue_qk(false);          // look-ahead Q K^T (its S buffer was freed by P V_{g-1})
         const int st = g % KV_STAGES;
         const uint32_t vs = kv_s + st * C::KV_STAGE + KV_TILE_BYTES;
         mbar_wait(p_ready(SB(g)), SPH(g));                               // P_g in TMEM, O rescaled (or read out), S[SB(g)] consumed
