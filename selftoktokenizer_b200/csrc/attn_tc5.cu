@@ -1,5 +1,7 @@
-// Joint attention of the MMDiT on tcgen05 tensor cores with TMEM accumulators (sm_100a), head_dim 64, single-pass
-// 16-bit operands (IEEE half or bf16), fp32 softmax.
+// Joint attention of the MMDiT on tcgen05 tensor cores with TMEM accumulators (sm_100a), head_dim 64, fp32 softmax.
+// Operands: single-pass 16-bit (IEEE half or bf16), or split bf16 ("bf16x3": hi*hi + hi*lo + lo*hi into the same TMEM
+// accumulators for both products, fp32-faithful).  The split mode keeps 2 CTAs per SM by giving up the second Q buffer and
+// two of the four K/V stages (one CTA per SM with deeper buffers measured 1362 ms vs 1025 ms per 50-step decode).
 //
 //   grid           persistent: 2 CTAs per SM (100 KiB smem, 256 TMEM columns each) walk the work items (image, head, 128-query
 //                  tile), query tile fastest so that co-running CTAs share one (image, head)'s K / V in L2.  All roles follow
@@ -22,7 +24,7 @@
 //
 // Measured at S = 768, batch 64, 24 heads: 520 us (first version: one CTA per item, P through smem) -> 410-445 us.
 //
-// Same contract as attn_tc.cu (sd3/mmdit.py:521-531, sd3/other_impls.py:37-45): dense non-causal attention over the joint
+// Contract (sd3/mmdit.py:521-531, sd3/other_impls.py:37-45): dense non-causal attention over the joint
 // [context prefix ; image] sequence; rows < ctx_rows only see keys < ctx_keys (renderer rule, mmdit.py:1581).
 #include "common.cuh"
 #include "kernels.h"
@@ -58,14 +60,19 @@ constexpr int XCH_BYTES = 6 * BQ * 4;               // row-max exchange (2 parit
 // hi*hi + hi*lo + lo*hi of bf16 planes accumulated into the same TMEM tile -- Q, K, V arrive as hi and lo planes (twice the
 // shared memory: one CTA per SM, three K/V stages), P is split in registers and its lo half goes into the S columns the hi
 // half leaves free.
+// split mode at 2 CTAs per SM: one Q buffer and two K/V stages (100 KiB per CTA) instead of 2 + 3 (160 KiB, one CTA per SM)
+#ifndef SELFTOK_ATTN5_SPLIT_CTAS
+#define SELFTOK_ATTN5_SPLIT_CTAS 2
+#endif
 template <int NSPLIT> struct A5 {
   static constexpr int PL = NSPLIT == 3 ? 2 : 1;                        // operand planes
-  static constexpr int KV_STAGES = NSPLIT == 3 ? 3 : 4;
+  static constexpr int MIN_CTAS = NSPLIT == 3 ? SELFTOK_ATTN5_SPLIT_CTAS : 2;
+  static constexpr int KV_STAGES = NSPLIT == 3 ? (MIN_CTAS == 2 ? 2 : 3) : 4;
+  static constexpr int Q_STAGES = (NSPLIT == 3 && MIN_CTAS == 2) ? 1 : 2;
   static constexpr int Q_STAGE = PL * Q_BYTES;                          // [hi | lo]
   static constexpr int KV_STAGE = PL * 2 * KV_TILE_BYTES;               // [K hi | V hi | K lo | V lo]
-  static constexpr int SMEM_TILES = 2 * Q_STAGE + KV_STAGES * KV_STAGE; // 96 KiB / 160 KiB (P lives in TMEM)
+  static constexpr int SMEM_TILES = Q_STAGES * Q_STAGE + KV_STAGES * KV_STAGE;   // 96 KiB (P lives in TMEM)
   static constexpr int SMEM_BYTES = SMEM_TILES + 1024 + 256 + XCH_BYTES;   // tiles + alignment slack + barriers + exchange
-  static constexpr int MIN_CTAS = NSPLIT == 3 ? 1 : 2;
 };
 constexpr int TMEM_COLS = 256;      // S0 [0,64) | S1 [64,128) | O0 [128,192) | O1 [192,256); P_g overwrites half of S_g in place
 constexpr int NUM_THREADS = 64 + 8 * 32;        // TMA warp, MMA warp, 8 softmax warps
@@ -237,7 +244,9 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_s = base;                                  // Q buffer qb at q_s + qb * Q_STAGE (hi plane, lo plane)
-  const uint32_t kv_s = base + 2 * C::Q_STAGE;                // stage st at kv_s + st * KV_STAGE: K hi, V hi (, K lo, V lo)
+  constexpr int QS = C::Q_STAGES;
+  static_assert(!SPLIT_ISSUE || QS == 2, "the two-issuer experiment prefetches Q one item ahead");
+  const uint32_t kv_s = base + QS * C::Q_STAGE;               // stage st at kv_s + st * KV_STAGE: K hi, V hi (, K lo, V lo)
   const uint32_t bars = kv_s + KV_STAGES * C::KV_STAGE;
   // every per-tile barrier exists twice (tile parity) so that no waiter can be lapped by two phases
   auto q_full = [&](int qb) { return bars + 8u * qb; };
@@ -307,8 +316,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   // S[SB(gq)] = Q K_gq^T, then advance the cursor.  wait_free: the caller is not the P V issuer, so the buffer's previous
   // occupant (tile gq - NSB) must be seen retired explicitly instead of through the issue order of one thread.
   auto issue_qk = [&](bool wait_free) {
-    const int qb = cq.n & 1, st = gq % KV_STAGES;
-    if (cq.j == 0) mbar_wait(q_full(qb), (cq.n >> 1) & 1);
+    const int qb = cq.n % QS, st = gq % KV_STAGES;
+    if (cq.j == 0) mbar_wait(q_full(qb), (cq.n / QS) & 1);
     mbar_wait(kv_full(st), (gq / KV_STAGES) & 1);
     if (wait_free && gq >= NSB) mbar_wait(pv_done(SB(gq)), SPH(gq - NSB));
     tc_fence_after();
@@ -332,8 +341,8 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     if (lane == 0) {
       auto load_q = [&](int item, int n) {                              // n = CTA-local item number
         const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
-        const int qb = n & 1;
-        mbar_wait(q_empty(qb), ((n >> 1) & 1) ^ 1);
+        const int qb = n % QS;
+        mbar_wait(q_empty(qb), ((n / QS) & 1) ^ 1);
         mbar_expect_tx(q_full(qb), C::Q_STAGE);
         tma_load_2d(q_s + qb * C::Q_STAGE, &map_q, q_full(qb), h * HD, b * S + qt * BQ);
         if (NSPLIT == 3) tma_load_2d(q_s + qb * C::Q_STAGE + Q_BYTES, &map_q_lo, q_full(qb), h * HD, b * S + qt * BQ);
@@ -360,13 +369,13 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         int gt = 0, pend_item = -1, pend_n = 0;
         if (ct.item < n_items) load_q(ct.item, 0);
         while (cq.item < n_items) {
-          if (pend_item >= 0 && mbar_test(q_empty(pend_n & 1), ((pend_n >> 1) & 1) ^ 1)) { load_q(pend_item, pend_n); pend_item = -1; }
+          if (pend_item >= 0 && mbar_test(q_empty(pend_n % QS), ((pend_n / QS) & 1) ^ 1)) { load_q(pend_item, pend_n); pend_item = -1; }
           if (ct.item < n_items) {
             if (ct.j == 0 && ct.item + (int)gridDim.x < n_items) {
               while (pend_item >= 0) {                                    // short items: the previous prefetch is still owed
                 if (gq < gt && pend_n != cq.n) issue_qk(true);
                 else { load_q(pend_item, pend_n); pend_item = -1; }
-                if (pend_item >= 0 && mbar_test(q_empty(pend_n & 1), ((pend_n >> 1) & 1) ^ 1)) { load_q(pend_item, pend_n); pend_item = -1; }
+                if (pend_item >= 0 && mbar_test(q_empty(pend_n % QS), ((pend_n / QS) & 1) ^ 1)) { load_q(pend_item, pend_n); pend_item = -1; }
               }
               pend_item = ct.item + gridDim.x; pend_n = ct.n + 1;
             }
@@ -383,23 +392,11 @@ attention_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       int g = 0, n = 0;
       if (!SPLIT_ISSUE && (int)blockIdx.x < n_items) load_q(blockIdx.x, 0);
       for (int item = blockIdx.x; !SPLIT_ISSUE && item < n_items; item += gridDim.x, ++n) {
-        const int qt = item % nq, h = (item / nq) % p.H, b = item / (nq * p.H);
-        const int row0 = b * S;                                         // first row of this image in the [B*S, 3*H*64] matrix
-        const int n_tiles = item_tiles(qt);
-        if (item + (int)gridDim.x < n_items) load_q(item + gridDim.x, n + 1);   // next item's Q, one item ahead
-        for (int j = 0; j < n_tiles; ++j, ++g) {
-          const int st = g % KV_STAGES;
-          const uint32_t ph = (g / KV_STAGES) & 1;
-          mbar_wait(kv_empty(st), ph ^ 1);
-          const uint32_t ks = kv_s + st * C::KV_STAGE;
-          mbar_expect_tx(kv_full(st), C::KV_STAGE);
-          tma_load_2d(ks, &map_kv, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
-          tma_load_2d(ks + KV_TILE_BYTES, &map_kv, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
-          if (NSPLIT == 3) {
-            tma_load_2d(ks + 2 * KV_TILE_BYTES, &map_kv_lo, kv_full(st), (p.H + h) * HD, row0 + j * BKV);
-            tma_load_2d(ks + 3 * KV_TILE_BYTES, &map_kv_lo, kv_full(st), (2 * p.H + h) * HD, row0 + j * BKV);
-          }
-        }
+        const int n_tiles = item_tiles(item % nq);
+        const bool more = item + (int)gridDim.x < n_items;
+        if (QS == 2 && more) load_q(item + gridDim.x, n + 1);            // next item's Q, one item ahead
+        for (int j = 0; j < n_tiles; ++j, ++g) load_kv(item, j, g);
+        if (QS == 1 && more) load_q(item + gridDim.x, n + 1);            // one Q buffer: free once this item's last Q K^T retired
       }
     }
   } else if (warp == 1) {
@@ -620,7 +617,7 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
   Attn5Params p{out, B, S, H, ctx_rows, ctx_keys, fp16, 0.125f * 1.4426950408889634f};
   const int n_items = ((S + BQ - 1) / BQ) * H * B;
   if (qkv_lo) {
-    dim3 grid(std::min(n_items, g_num_sms));                         // split mode: one (160 KiB) CTA per SM
+    dim3 grid(std::min(n_items, A5<3>::MIN_CTAS * g_num_sms));
     attention_tc5_kernel<false, 3><<<grid, NUM_THREADS, A5<3>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
   } else {
     dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
