@@ -156,9 +156,11 @@ int selftok_render_host(selftok_handle_t h, const int64_t* tokens_host, int B, f
  * resets it (< 0: CUDA error). */
 int64_t selftok_id_errors(selftok_handle_t h, void* stream);
 
-/* ---- SD3 VAE decoder on the device: replaces `self.vae.decode(pred_x0_out)` of SelftokPipeline.decoding /
- * decoding_with_renderer (SelftokPipeline.py:288,316; architecture: sd3/sd3_impls.py:314-444).  Weights are loaded under the
- * in-tree SDVAE key names ("decoder.conv_in.weight", "decoder.up.3.block.0.norm1.bias", ...), fp32, one call per tensor.
+/* ---- SD3 VAE on the device: replaces `self.vae.decode(pred_x0_out)` of SelftokPipeline.decoding /
+ * decoding_with_renderer (SelftokPipeline.py:288,316) and `self.vae.encode(images)[0].mode()` of SelftokPipeline.encoding (:215);
+ * architecture: sd3/sd3_impls.py:314-444.  Weights are loaded under the in-tree SDVAE key names ("decoder.conv_in.weight",
+ * "decoder.up.3.block.0.norm1.bias", "encoder.down.0.downsample.conv.weight", ...), fp32, one call per tensor; either half may
+ * be omitted (the matching entry point then returns SELFTOK_ERR_MISSING_TENSOR).
  * selftok_vae_decode: z_dev [B,16,h,w] fp32 in VAE latent space (after SD3LatentFormat.process_out), h = w in {8,16,32,64}
  * -> out_dev [B,3,8h,8w] fp32; norm_ip != 0 applies the pipeline's clamp to [-1,1] + rescale to [0,1]. */
 typedef struct selftok_vae* selftok_vae_t;
@@ -167,6 +169,10 @@ int selftok_vae_destroy(selftok_vae_t v);
 int selftok_vae_load_tensor(selftok_vae_t v, const char* name, const void* data, int ndim, const int64_t* shape, int is_device);
 int selftok_vae_finalize(selftok_vae_t v, void* stream);
 int selftok_vae_decode(selftok_vae_t v, const float* z_dev, int B, int h, int w, float* out_dev, int norm_ip, void* stream);
+/* images_dev [B,3,H,W] fp32 in [-1,1], H = W in {128,256,512} -> mean_out_dev [B,16,H/8,W/8] fp32 (the distribution's mode, VAE
+ * latent space: apply SD3LatentFormat.process_in afterwards); logvar_out_dev (same shape) may be NULL. */
+int selftok_vae_encode(selftok_vae_t v, const float* images_dev, int B, int H, int W, float* mean_out_dev, float* logvar_out_dev,
+                       void* stream);
 int64_t selftok_vae_device_bytes(selftok_vae_t v);
 
 /* ---- activation workspace.  By default the library allocates ONE device block per operation class (0 = encode,

@@ -163,6 +163,16 @@ def gen_vae_tiny():
     save("vae_tiny", dec=dec, moments=mom)
 
 
+def gen_vae_enc128():
+    """The reference's VAEEncoder at the shipped width (ch = 128) on two seeded 128 x 128 images: the direct pin of the device
+    VAE encoder (csrc/vae.cu selftok_vae_encode) and of oracle/vae_oracle.encode_moments at full width."""
+    vae = ref_vae(128)
+    x = synth.synth_tensor("golden.vae.x128", (2, 3, 128, 128), "emb", 0.5)
+    with torch.no_grad():
+        mom = vae.encoder(x)
+    save("vae_enc128", moments=mom)
+
+
 def gen_pixels_tiny():
     """Pixel fixture of the reduced geometry: the reference's own 50-step result (tests/golden/tiny.npz) through the
     reference SDVAE (full size, ch = 128) exactly as SelftokPipeline.decoding finishes (process_out -> vae.decode -> norm_ip)."""
@@ -385,6 +395,8 @@ if __name__ == "__main__":
             gen_tiny_datasize()
         elif w == "vae_tiny":
             gen_vae_tiny()
+        elif w == "vae_enc128":
+            gen_vae_enc128()
         elif w == "tiny_pixels":
             gen_pixels_tiny()
         elif w == "full_pixels":

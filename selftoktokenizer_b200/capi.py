@@ -27,7 +27,7 @@ SYMBOLS = [
     "selftok_render_host", "selftok_id_errors", "selftok_workspace_bytes", "selftok_set_workspace", "selftok_last_launch_count", "selftok_device_bytes", "selftok_set_use_graph",
     "selftok_set_profile", "selftok_get_profile", "selftok_k_linear_f32", "selftok_k_linear_tc", "selftok_k_set_gemm_ctas", "selftok_k_ln_mod_f32", "selftok_k_attention_f32",
     "selftok_k_attention_tc",
-    "selftok_vae_create", "selftok_vae_destroy", "selftok_vae_load_tensor", "selftok_vae_finalize", "selftok_vae_decode", "selftok_vae_device_bytes",
+    "selftok_vae_create", "selftok_vae_destroy", "selftok_vae_load_tensor", "selftok_vae_finalize", "selftok_vae_decode", "selftok_vae_encode", "selftok_vae_device_bytes",
 ]
 
 
@@ -99,6 +99,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.selftok_vae_load_tensor.argtypes = [vp, C.c_char_p, vp, i32, C.POINTER(i64), i32]
     lib.selftok_vae_finalize.argtypes = [vp, vp]
     lib.selftok_vae_decode.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp]
+    lib.selftok_vae_encode.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
     lib.selftok_vae_device_bytes.argtypes = [vp]
     lib.selftok_vae_device_bytes.restype = i64
     for name in SYMBOLS:
@@ -444,10 +445,11 @@ class Engine:
 
 
 class VaeDecoder:
-    """SD3 VAE decoder on the device (`selftok_vae_t`): the `vae.decode` step of SelftokPipeline.decoding.  `state_dict` uses the
-    in-tree SDVAE key names (decoder.*); `from_diffusers_keys` maps a diffusers AutoencoderKL state dict onto them."""
+    """SD3 VAE on the device (`selftok_vae_t`): the `vae.decode` step of SelftokPipeline.decoding and -- when the state dict also
+    holds encoder.* tensors -- the `vae.encode(...).mode()` step of SelftokPipeline.encoding.  `state_dict` uses the in-tree
+    SDVAE key names (decoder.* / encoder.*); `from_diffusers_keys` maps a diffusers AutoencoderKL state dict onto them."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", ch: int = 128):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda:0", ch: int = 128, halves=("decoder.", "encoder.")):
         self.lib = load_library()
         if not torch.cuda.is_available():
             raise SelftokError("no CUDA device: selftok_b200 has no CPU fallback")
@@ -457,7 +459,7 @@ class VaeDecoder:
         self.h = h
         try:
             for name, t in state_dict.items():
-                if not name.startswith("decoder.") or not torch.is_tensor(t):
+                if not name.startswith(tuple(halves)) or not torch.is_tensor(t):
                     continue
                 t = t.detach().to(torch.float32).contiguous()
                 if t.is_cuda and t.device != self.device:
@@ -481,9 +483,23 @@ class VaeDecoder:
             check(self.lib.selftok_vae_decode(self.h, z.data_ptr(), B, h, w, out.data_ptr(), int(norm_ip), _stream_ptr(self.device)))
         return out
 
+    def encode(self, images: torch.Tensor, return_logvar: bool = False):
+        """images [B,3,H,H] in [-1,1] -> the latent distribution's mode [B,16,H/8,H/8] fp32 (VAE latent space, before
+        SD3LatentFormat.process_in); with return_logvar also the log-variance."""
+        if images.dim() != 4 or images.shape[1] != 3 or images.shape[2] != images.shape[3]:
+            raise SelftokError(f"VaeDecoder.encode: expected [B,3,H,H] images, got {tuple(images.shape)}")
+        x = images.to(device=self.device, dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        mean = torch.empty(B, 16, H // 8, W // 8, dtype=torch.float32, device=self.device)
+        logvar = torch.empty_like(mean) if return_logvar else None
+        with torch.cuda.device(self.device):
+            check(self.lib.selftok_vae_encode(self.h, x.data_ptr(), B, H, W, mean.data_ptr(), logvar.data_ptr() if return_logvar else None,
+                                              _stream_ptr(self.device)))
+        return (mean, logvar) if return_logvar else mean
+
     @staticmethod
     def from_diffusers_keys(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
-        """diffusers AutoencoderKL decoder keys -> SDVAE keys (the same weights under the other naming: up_blocks are listed
+        """diffusers AutoencoderKL keys -> SDVAE keys (the same weights under the other naming: decoder up_blocks are listed
         lowest resolution first there, attention projections are Linear [C,C] instead of 1x1 convs)."""
         out = {}
         ren = {"conv_norm_out": "norm_out", "mid_block.resnets.0": "mid.block_1", "mid_block.resnets.1": "mid.block_2",
@@ -491,12 +507,19 @@ class VaeDecoder:
                "mid_block.attentions.0.to_k": "mid.attn_1.k", "mid_block.attentions.0.to_v": "mid.attn_1.v",
                "mid_block.attentions.0.to_out.0": "mid.attn_1.proj_out"}
         for k, v in sd.items():
-            if not k.startswith("decoder."):
+            half = "decoder." if k.startswith("decoder.") else "encoder." if k.startswith("encoder.") else None
+            if half is None:
                 continue
-            n = k[len("decoder."):]
+            n = k[len(half):]
             for a, b in ren.items():
                 if n.startswith(a + "."):
                     n = b + n[len(a):]
+            if n.startswith("down_blocks."):
+                parts = n.split(".")
+                if parts[2] == "resnets":
+                    n = f"down.{parts[1]}.block.{parts[3]}." + ".".join(parts[4:])
+                elif parts[2] == "downsamplers":
+                    n = f"down.{parts[1]}.downsample." + ".".join(parts[4:])
             if n.startswith("up_blocks."):
                 parts = n.split(".")
                 lvl = 3 - int(parts[1])
@@ -507,7 +530,7 @@ class VaeDecoder:
             n = n.replace("conv_shortcut", "nin_shortcut")
             if ".attn_1." in n and n.endswith(".weight") and v.dim() == 2:
                 v = v[:, :, None, None]
-            out["decoder." + n] = v
+            out[half + n] = v
         return out
 
     def close(self) -> None:

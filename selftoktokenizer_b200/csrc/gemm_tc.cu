@@ -263,7 +263,11 @@ struct GemmParams {
   // tap * C + c.  conv_C == 0: plain GEMM.  The A tile of k-block kb (tap = kb / (C / 64), channels chunk = kb % (C / 64)) is the
   // 4-D TMA box {64 channels, bw pixels, bh rows, bn images} (bw bh bn = 128) shifted by the tap offset; out-of-image elements
   // are zero-filled by the TMA unit -- exactly the padding.
-  int conv_C = 0, conv_H = 0, conv_W = 0;
+  // conv_stride == 2 (Downsample, sd3_impls.py:287-298: zero pad right / bottom, 3x3 stride 2): the planes hold the four
+  // polyphase components of the input, [image * 4 + (py * 2 + px)][H_out][W_out][C] with phase(py, px)[y][x] = in[2y + py][2x + px];
+  // tap (dy, dx) reads phase (dy & 1, dx & 1) shifted by (dy >> 1, dx >> 1) -- unit-stride boxes again, the zero fill past the last
+  // row / column is the one-sided padding.  conv_H / conv_W are the OUTPUT dims.
+  int conv_C = 0, conv_H = 0, conv_W = 0, conv_stride = 1;
 };
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
@@ -569,9 +573,11 @@ gemm_tc2_kernel(const __grid_constant__ TcMaps maps0, const __grid_constant__ Tc
           if (leader) mbar_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
           if (pp.conv_C > 0) {
             const int tap = kb / chunks, c0 = (kb - tap * chunks) * BK;
-            const int x0 = cx + tap % 3 - 1, y0 = cy + tap / 3 - 1;
-            tma_load_4d_2sm(sa, &mp.a_hi, fb, c0, x0, y0, cb);
-            if (NSPLIT == 3) tma_load_4d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, c0, x0, y0, cb);
+            const int dy = tap / 3, dx = tap - dy * 3;
+            int x0 = cx + dx - 1, y0 = cy + dy - 1, n0 = cb;
+            if (pp.conv_stride == 2) { x0 = cx + (dx >> 1); y0 = cy + (dy >> 1); n0 = cb * 4 + (dy & 1) * 2 + (dx & 1); }
+            tma_load_4d_2sm(sa, &mp.a_hi, fb, c0, x0, y0, n0);
+            if (NSPLIT == 3) tma_load_4d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, c0, x0, y0, n0);
           } else {
             tma_load_2d_2sm(sa, &mp.a_hi, fb, kb * BK, m_row);
             if (NSPLIT == 3) tma_load_2d_2sm(sa + A_TILE_BYTES, &mp.a_lo, fb, kb * BK, m_row);
@@ -772,13 +778,14 @@ static int check_problem(const TcProblem& q, int nsplit, int fp16) {
     const int64_t hw = (int64_t)q.conv_H * q.conv_W;
     STK_CHECK(q.M % hw == 0 && (hw % BM == 0 || BM % hw == 0) && (q.conv_W >= BM || hw < BM || q.conv_H % (BM / q.conv_W) == 0), -2,
               "gemm_tc conv: 128-pixel tiles must be part of a row, whole rows of one image, or whole images");
+    STK_CHECK(q.conv_stride == 1 || (q.conv_stride == 2 && hw % BM == 0), -2, "gemm_tc conv: stride 2 needs >= 128 output pixels per image");
   }
   return 0;
 }
 
 static int make_maps(TcMaps* m, const TcProblem& q, int nsplit, int fp16, int b_box) {
   const bool conv = q.conv_C > 0;
-  const int64_t imgs = conv ? q.M / ((int64_t)q.conv_H * q.conv_W) : 0;
+  const int64_t imgs = conv ? q.M / ((int64_t)q.conv_H * q.conv_W) * (q.conv_stride == 2 ? 4 : 1) : 0;   // stride 2: 4 phase planes per image
   if (conv) STK_TRY(make_map_nhwc(&m->a_hi, q.A_hi, imgs, q.conv_H, q.conv_W, q.conv_C, fp16));
   else STK_TRY(make_map(&m->a_hi, q.A_hi, q.M, q.K, BM, fp16));
   STK_TRY(make_map(&m->b_hi, q.W_hi, q.N, q.K, b_box, fp16));
@@ -822,7 +829,7 @@ int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream
   STK_TRY(make_maps(&m0, probs[0], nsplit, fp16, BN / 2));
   auto mk_params = [&](const TcProblem& q) {
     GemmParams g{q.M, q.N, q.K, fp16, q.ep};
-    g.conv_C = q.conv_C; g.conv_H = q.conv_H; g.conv_W = q.conv_W;
+    g.conv_C = q.conv_C; g.conv_H = q.conv_H; g.conv_W = q.conv_W; g.conv_stride = q.conv_stride;
     return g;
   };
   GemmParams p0 = mk_params(probs[0]);

@@ -1,7 +1,10 @@
-// SD3 16-channel VAE DECODER on the device: the step after the token path in SelftokPipeline.decoding /
-// decoding_with_renderer (`self.vae.decode(pred_x0_out)`, SelftokPipeline.py:288,316).  Architecture as vendored in the
-// reference tree (VAEDecoder, mimogpt/models/selftok/sd3/sd3_impls.py:314-444): conv_in -> mid (ResnetBlock, AttnBlock,
-// ResnetBlock) -> 4 levels of 3 ResnetBlocks (+ nearest-2x Upsample + conv) -> GroupNorm -> SiLU -> conv_out.
+// SD3 16-channel VAE on the device: the steps either side of the token path in SelftokPipeline --
+// `self.vae.encode(images)[0].mode()` before the encoder (SelftokPipeline.py:215) and `self.vae.decode(pred_x0_out)` after the
+// sampler / renderer (:288,316).  Architecture as vendored in the reference tree (mimogpt/models/selftok/sd3/sd3_impls.py):
+//   VAEDecoder (:388-444)  conv_in -> mid (ResnetBlock, AttnBlock, ResnetBlock) -> 4 levels of 3 ResnetBlocks (+ nearest-2x
+//                          Upsample + conv) -> GroupNorm -> SiLU -> conv_out
+//   VAEEncoder (:314-385)  conv_in -> 4 levels of 2 ResnetBlocks (+ Downsample: zero pad right / bottom, 3x3 stride-2 conv) -> mid
+//                          -> GroupNorm -> SiLU -> conv_out (mean | logvar)
 //
 //   layout        NHWC.  The residual stream is fp32 [B, H, W, C]; every convolution / 1x1 projection reads its input as
 //                 16-bit operand planes (bf16 hi + lo: the fp32-faithful split mode, three MMAs per product) written by the
@@ -9,6 +12,8 @@
 //   3x3 convs     implicit GEMM on the tcgen05 SM-pair kernel of gemm_tc.cu: A tile = 4-D TMA box of the NHWC planes shifted by
 //                 the tap offset (the TMA unit's out-of-bounds zero fill IS the padding), K = 9 C, weights repacked to
 //                 [Cout, (ky, kx), Cin]; bias and the residual add (x + h, ResnetBlock.forward :256) in the GEMM epilogue.
+//   stride-2 conv the input is written as its four polyphase planes (space_to_depth_planes_kernel); every tap is then a
+//                 unit-stride box of one phase plane, and the zero fill past the last row / column is the one-sided padding.
 //   GroupNorm     32 groups, eps 1e-6, affine; two deterministic passes (per-chunk partial sums in a fixed order, then
 //                 normalise + SiLU + plane output) -- no atomics.
 //   attention     the single-head 512-channel block of the middle (AttnBlock.forward :276-287): per image S = Q K^T and
@@ -130,6 +135,24 @@ __global__ void __launch_bounds__(256) upsample2x_planes_kernel(const float* __r
     reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack2_resid_bf16(v.x, v.y, p0), pack2_resid_bf16(v.z, v.w, p1));
   }
 }
+// Downsample input: fp32 NHWC [B, H, W, C] -> polyphase operand planes [B * 4 + (py * 2 + px)][H / 2][W / 2][C] with
+// phase(py, px)[y][x] = in[2y + py][2x + px] (the A operand layout of the stride-2 implicit GEMM, gemm_tc.cu)
+__global__ void __launch_bounds__(256) space_to_depth_planes_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, int B, int H,
+                                                                    int W, int C) {
+  const int c4n = C >> 2, Ho = H >> 1, Wo = W >> 1;
+  const int64_t total4 = (int64_t)B * H * W * c4n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % c4n);
+    const int64_t pix = i / c4n;                                   // output order: (b, phase, yo, xo)
+    const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho);
+    const int ph = (int)((pix / ((int64_t)Wo * Ho)) & 3);
+    const int64_t b = pix / ((int64_t)Wo * Ho * 4);
+    const float4 v = reinterpret_cast<const float4*>(x)[((b * H + (2 * yo + (ph >> 1))) * W + (2 * xo + (ph & 1))) * c4n + c4];
+    const uint32_t p0 = pack2_sat16(v.x, v.y, false), p1 = pack2_sat16(v.z, v.w, false);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(p0, p1);
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack2_resid_bf16(v.x, v.y, p0), pack2_resid_bf16(v.z, v.w, p1));
+  }
+}
 // row softmax of the attention scores: P = softmax(S * scale) [rows, n] fp32 -> bf16 hi / lo planes; one warp per row
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ s, bf16* __restrict__ hi, bf16* __restrict__ lo, int64_t rows, int n,
                                                            float scale) {
@@ -164,6 +187,16 @@ __global__ void nhwc4_to_nchw3_kernel(const float* __restrict__ x, float* __rest
     out[i] = v;
   }
 }
+// channels [c0, c0 + Cn) of an fp32 NHWC tensor [B, HW, Cs] -> NCHW [B, Cn, HW] (the mean / logvar halves of the encoder's conv_out)
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int HW, int Cs, int c0, int Cn) {
+  const int64_t total = (int64_t)B * Cn * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i % HW;
+    const int c = (int)((i / HW) % Cn);
+    const int64_t b = i / ((int64_t)Cn * HW);
+    out[i] = x[(b * HW + p) * Cs + c0 + c];
+  }
+}
 // conv weight [Cout, Cin, kh, kw] fp32 -> GEMM operand [Npad, kh*kw*Cpad] fp32 with K index (ky*kw + kx) * Cpad + c (zero padding)
 __global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps, int Npad, int Cpad) {
   const int64_t total = (int64_t)Npad * taps * Cpad;
@@ -186,7 +219,7 @@ struct VaeW {            // one convolution / projection: packed planes + fp32 b
 struct selftok_vae {
   int device = 0, ch = 128;
   int mult[4] = {1, 2, 4, 4};
-  bool finalized = false;
+  bool finalized = false, has_dec = false, has_enc = false;
   std::unordered_map<std::string, std::pair<float*, std::vector<int64_t>>> raw;      // loaded fp32 tensors (freed at finalize unless norm / bias)
   std::unordered_map<std::string, VaeW> conv;
   std::vector<void*> allocs;
@@ -308,18 +341,38 @@ extern "C" __attribute__((visibility("default"))) int selftok_vae_finalize(selft
   STK_CUDA(cudaSetDevice(v->device));
   cudaStream_t s = (cudaStream_t)stream;
   const int ch = v->ch;
-  std::vector<std::string> convs = {"decoder.conv_in", "decoder.conv_out", "decoder.mid.attn_1.q", "decoder.mid.attn_1.k", "decoder.mid.attn_1.v",
-                                    "decoder.mid.attn_1.proj_out"};
-  for (const char* b : {"decoder.mid.block_1", "decoder.mid.block_2"})
-    for (auto& n : resnet_names(b, false)) convs.push_back(n);
-  int cin = ch * v->mult[3];
-  for (int lvl = 3; lvl >= 0; --lvl) {
-    const int cout = ch * v->mult[lvl];
-    for (int b = 0; b < 3; ++b) {
-      for (auto& n : resnet_names("decoder.up." + std::to_string(lvl) + ".block." + std::to_string(b), cin != cout)) convs.push_back(n);
-      cin = cout;
+  v->has_dec = v->raw.count("decoder.conv_in.weight") > 0;
+  v->has_enc = v->raw.count("encoder.conv_in.weight") > 0;
+  STK_CHECK(v->has_dec || v->has_enc, SELFTOK_ERR_MISSING_TENSOR, "selftok_vae_finalize: neither decoder.* nor encoder.* tensors were loaded");
+  std::vector<std::string> convs;
+  auto add_mid = [&](const std::string& p) {
+    for (const char* n : {".conv_in", ".conv_out", ".mid.attn_1.q", ".mid.attn_1.k", ".mid.attn_1.v", ".mid.attn_1.proj_out"}) convs.push_back(p + n);
+    for (const char* b : {".mid.block_1", ".mid.block_2"})
+      for (auto& n : resnet_names(p + b, false)) convs.push_back(n);
+  };
+  if (v->has_dec) {
+    add_mid("decoder");
+    int cin = ch * v->mult[3];
+    for (int lvl = 3; lvl >= 0; --lvl) {
+      const int cout = ch * v->mult[lvl];
+      for (int b = 0; b < 3; ++b) {
+        for (auto& n : resnet_names("decoder.up." + std::to_string(lvl) + ".block." + std::to_string(b), cin != cout)) convs.push_back(n);
+        cin = cout;
+      }
+      if (lvl != 0) convs.push_back("decoder.up." + std::to_string(lvl) + ".upsample.conv");
     }
-    if (lvl != 0) convs.push_back("decoder.up." + std::to_string(lvl) + ".upsample.conv");
+  }
+  if (v->has_enc) {
+    add_mid("encoder");
+    int cin = ch;
+    for (int lvl = 0; lvl < 4; ++lvl) {
+      const int cout = ch * v->mult[lvl];
+      for (int b = 0; b < 2; ++b) {
+        for (auto& n : resnet_names("encoder.down." + std::to_string(lvl) + ".block." + std::to_string(b), cin != cout)) convs.push_back(n);
+        cin = cout;
+      }
+      if (lvl != 3) convs.push_back("encoder.down." + std::to_string(lvl) + ".downsample.conv");
+    }
   }
   for (auto& n : convs) STK_TRY(pack_conv(v, n, s));
   v->finalized = true;
@@ -337,7 +390,7 @@ static const float* vget(selftok_vae* v, const std::string& name) {
   return it == v->raw.end() ? nullptr : it->second.first;
 }
 // y = conv(planes) (+ resid) -> out (fp32 NHWC [M, N]); taps == 9: implicit GEMM over [B, H, W, Cpad] planes
-static int vconv(VaeCtx& c, const std::string& name, const bf16* a_hi, const bf16* a_lo, int H, int W, float* out, const float* resid) {
+static int vconv(VaeCtx& c, const std::string& name, const bf16* a_hi, const bf16* a_lo, int H, int W, float* out, const float* resid, int stride = 1) {
   auto it = c.v->conv.find(name);
   STK_CHECK(it != c.v->conv.end(), SELFTOK_ERR_STATE, "VAE conv not packed");
   const VaeW& w = it->second;
@@ -345,7 +398,7 @@ static int vconv(VaeCtx& c, const std::string& name, const bf16* a_hi, const bf1
   ep.bias = w.bias; ep.out = out; ep.ldo = w.Npad;
   if (resid) { ep.mode = EPI_RESID; ep.resid = resid; }
   TcProblem q{a_hi, a_lo, w.hi, w.lo, (int64_t)c.B * H * W, w.Npad, w.K, ep};
-  if (w.taps == 9) { q.conv_C = w.Cpad; q.conv_H = H; q.conv_W = W; }
+  if (w.taps == 9) { q.conv_C = w.Cpad; q.conv_H = H; q.conv_W = W; q.conv_stride = stride; }      // stride 2: H, W = output dims
   return launch_gemm_tc_grouped(&q, 1, 3, c.s, 0);
 }
 // GroupNorm (+ SiLU) of the fp32 NHWC stream x [B, HW, C] into the operand planes
@@ -383,6 +436,53 @@ static int vresnet(VaeCtx& c, const std::string& p, float*& x, float*& y, int H,
     STK_TRY(vconv(c, p + ".conv2", v->p_hi, v->p_lo, H, W, y, x));                     // y = x + conv2(.)   (y != x: conv1 output consumed)
   }
   std::swap(x, y);
+  return 0;
+}
+
+// the middle of both networks: ResnetBlock, AttnBlock, ResnetBlock at Cm channels on the [B, H, W] grid
+static int vmid(VaeCtx& c, const std::string& pre, float*& x, float*& y, int H, int W, int Cm) {
+  selftok_vae* v = c.v;
+  cudaStream_t s = c.s;
+  const int B = c.B;
+  STK_TRY(vresnet(c, pre + ".mid.block_1", x, y, H, W, Cm, Cm));
+  {
+    // AttnBlock (sd3_impls.py:276-287): h = norm(x); q, k, v = 1x1 convs; softmax(q k^T / sqrt(C)) v; x + proj_out(.)
+    const int64_t T = (int64_t)H * W;
+    STK_TRY(vnorm(c, pre + ".mid.attn_1.norm", x, T, Cm, false));
+    auto lin_planes = [&](const std::string& name, bf16* oh, bf16* ol) -> int {       // [B T, C] planes -> [B T, C] planes (+ bias)
+      const VaeW& wq = v->conv[name];
+      Epilogue ep;
+      ep.mode = EPI_SPLIT; ep.bias = wq.bias; ep.out_hi = oh; ep.out_lo = ol; ep.ldo = Cm;
+      TcProblem q{v->p_hi, v->p_lo, wq.hi, wq.lo, (int64_t)B * T, Cm, Cm, ep};
+      return launch_gemm_tc_grouped(&q, 1, 3, s, 0);
+    };
+    STK_TRY(lin_planes(pre + ".mid.attn_1.q", v->q_hi, v->q_lo));
+    STK_TRY(lin_planes(pre + ".mid.attn_1.k", v->k_hi, v->k_lo));
+    const VaeW& wv = v->conv[pre + ".mid.attn_1.v"];
+    for (int b = 0; b < B; ++b) {
+      const int64_t off = (int64_t)b * T * Cm;
+      // V^T [C, T] = W_v [C, C] . h_b^T  (operands swapped; the bias is added after P V: the rows of P sum to one)
+      Epilogue ev;
+      ev.mode = EPI_SPLIT; ev.out_hi = v->vt_hi + off; ev.out_lo = v->vt_lo + off; ev.ldo = T;
+      TcProblem qv{wv.hi, wv.lo, v->p_hi + off, v->p_lo + off, Cm, (int)T, Cm, ev};
+      STK_TRY(launch_gemm_tc_grouped(&qv, 1, 3, s, 0));
+      // S = Q_b K_b^T  [T, T] fp32
+      Epilogue es;
+      es.out = v->s_attn; es.ldo = T;
+      TcProblem qs{v->q_hi + off, v->q_lo + off, v->k_hi + off, v->k_lo + off, T, (int)T, Cm, es};
+      STK_TRY(launch_gemm_tc_grouped(&qs, 1, 3, s, 0));
+      softmax_rows_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(v->s_attn, v->pr_hi, v->pr_lo, T, (int)T, 1.0f / sqrtf((float)Cm));
+      count_launch();
+      // O_b = P V + b_v  [T, C] -> planes (A operand of proj_out)
+      Epilogue eo;
+      eo.mode = EPI_SPLIT; eo.bias = wv.bias; eo.out_hi = v->o_hi + off; eo.out_lo = v->o_lo + off; eo.ldo = Cm;
+      TcProblem qo{v->pr_hi, v->pr_lo, v->vt_hi + off, v->vt_lo + off, T, Cm, (int)T, eo};
+      STK_TRY(launch_gemm_tc_grouped(&qo, 1, 3, s, 0));
+    }
+    STK_TRY(vconv(c, pre + ".mid.attn_1.proj_out", v->o_hi, v->o_lo, H, W, y, x));     // y = x + proj_out(o)
+    std::swap(x, y);
+  }
+  STK_TRY(vresnet(c, pre + ".mid.block_2", x, y, H, W, Cm, Cm));
   return 0;
 }
 
@@ -431,6 +531,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_vae_decode(selftok
                                   void* stream) {
   STK_CHECK(v && z_dev && out_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_vae_decode: bad argument");
   STK_CHECK(v->finalized, SELFTOK_ERR_STATE, "selftok_vae_finalize has not been called");
+  STK_CHECK(v->has_dec, SELFTOK_ERR_MISSING_TENSOR, "selftok_vae_decode: no decoder.* tensors were loaded");
   STK_CHECK(h == w && (h == 8 || h == 16 || h == 32 || h == 64), SELFTOK_ERR_UNSUPPORTED, "VAE decode: square latents of side 8, 16, 32 or 64");
   STK_CUDA(cudaSetDevice(v->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -443,46 +544,7 @@ extern "C" __attribute__((visibility("default"))) int selftok_vae_decode(selftok
   count_launch();
   float *x = v->xa, *y = v->xb;
   STK_TRY(vconv(c, "decoder.conv_in", v->p_hi, v->p_lo, H, W, x, nullptr));
-  // middle
-  STK_TRY(vresnet(c, "decoder.mid.block_1", x, y, H, W, Cm, Cm));
-  {
-    // AttnBlock (sd3_impls.py:276-287): h = norm(x); q, k, v = 1x1 convs; softmax(q k^T / sqrt(C)) v; x + proj_out(.)
-    const int64_t T = (int64_t)H * W;
-    STK_TRY(vnorm(c, "decoder.mid.attn_1.norm", x, T, Cm, false));
-    auto lin_planes = [&](const std::string& name, bf16* oh, bf16* ol) -> int {       // [B T, C] planes -> [B T, C] planes (+ bias)
-      const VaeW& wq = v->conv[name];
-      Epilogue ep;
-      ep.mode = EPI_SPLIT; ep.bias = wq.bias; ep.out_hi = oh; ep.out_lo = ol; ep.ldo = Cm;
-      TcProblem q{v->p_hi, v->p_lo, wq.hi, wq.lo, (int64_t)B * T, Cm, Cm, ep};
-      return launch_gemm_tc_grouped(&q, 1, 3, s, 0);
-    };
-    STK_TRY(lin_planes("decoder.mid.attn_1.q", v->q_hi, v->q_lo));
-    STK_TRY(lin_planes("decoder.mid.attn_1.k", v->k_hi, v->k_lo));
-    const VaeW& wv = v->conv["decoder.mid.attn_1.v"];
-    for (int b = 0; b < B; ++b) {
-      const int64_t off = (int64_t)b * T * Cm;
-      // V^T [C, T] = W_v [C, C] . h_b^T  (operands swapped; the bias is added after P V: the rows of P sum to one)
-      Epilogue ev;
-      ev.mode = EPI_SPLIT; ev.out_hi = v->vt_hi + off; ev.out_lo = v->vt_lo + off; ev.ldo = T;
-      TcProblem qv{wv.hi, wv.lo, v->p_hi + off, v->p_lo + off, Cm, (int)T, Cm, ev};
-      STK_TRY(launch_gemm_tc_grouped(&qv, 1, 3, s, 0));
-      // S = Q_b K_b^T  [T, T] fp32
-      Epilogue es;
-      es.out = v->s_attn; es.ldo = T;
-      TcProblem qs{v->q_hi + off, v->q_lo + off, v->k_hi + off, v->k_lo + off, T, (int)T, Cm, es};
-      STK_TRY(launch_gemm_tc_grouped(&qs, 1, 3, s, 0));
-      softmax_rows_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(v->s_attn, v->pr_hi, v->pr_lo, T, (int)T, 1.0f / sqrtf((float)Cm));
-      count_launch();
-      // O_b = P V + b_v  [T, C] -> planes (A operand of proj_out)
-      Epilogue eo;
-      eo.mode = EPI_SPLIT; eo.bias = wv.bias; eo.out_hi = v->o_hi + off; eo.out_lo = v->o_lo + off; eo.ldo = Cm;
-      TcProblem qo{v->pr_hi, v->pr_lo, v->vt_hi + off, v->vt_lo + off, T, Cm, (int)T, eo};
-      STK_TRY(launch_gemm_tc_grouped(&qo, 1, 3, s, 0));
-    }
-    STK_TRY(vconv(c, "decoder.mid.attn_1.proj_out", v->o_hi, v->o_lo, H, W, y, x));     // y = x + proj_out(o)
-    std::swap(x, y);
-  }
-  STK_TRY(vresnet(c, "decoder.mid.block_2", x, y, H, W, Cm, Cm));
+  STK_TRY(vmid(c, "decoder", x, y, H, W, Cm));
   // upsampling
   int cin = Cm;
   for (int lvl = 3; lvl >= 0; --lvl) {
@@ -503,6 +565,52 @@ extern "C" __attribute__((visibility("default"))) int selftok_vae_decode(selftok
   STK_TRY(vconv(c, "decoder.conv_out", v->p_hi, v->p_lo, H, W, v->out4, nullptr));
   nhwc4_to_nchw3_kernel<<<blocks_for((int64_t)B * 3 * H * W), 256, 0, s>>>(v->out4, out_dev, B, H * W, norm_ip);
   count_launch();
+  STK_CUDA(cudaGetLastError());
+  return SELFTOK_OK;
+}
+
+// images_dev [B, 3, H, W] fp32 in [-1, 1] -> the latent distribution's parameters [B, 16, H/8, W/8] fp32 NCHW each (VAE latent
+// space, i.e. BEFORE SD3LatentFormat.process_in): mean_out_dev = `.mode()` (SelftokPipeline.py:215), logvar_out_dev optional.
+extern "C" __attribute__((visibility("default"))) int selftok_vae_encode(selftok_vae_t v, const float* images_dev, int B, int H, int W, float* mean_out_dev,
+                                  float* logvar_out_dev, void* stream) {
+  STK_CHECK(v && images_dev && mean_out_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_vae_encode: bad argument");
+  STK_CHECK(v->finalized, SELFTOK_ERR_STATE, "selftok_vae_finalize has not been called");
+  STK_CHECK(v->has_enc, SELFTOK_ERR_MISSING_TENSOR, "selftok_vae_encode: no encoder.* tensors were loaded");
+  STK_CHECK(H == W && (H == 128 || H == 256 || H == 512), SELFTOK_ERR_UNSUPPORTED, "VAE encode: square images of side 128, 256 or 512");
+  STK_CUDA(cudaSetDevice(v->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  STK_TRY(vae_ensure_ws(v, B, H / 8));
+  VaeCtx c{v, s, B};
+  const int ch = v->ch, Cm = ch * v->mult[3];
+  // conv_in: 3 image channels zero-padded to one 64-channel chunk
+  latent_to_planes_kernel<<<blocks_for((int64_t)B * H * W * 64), 256, 0, s>>>(images_dev, v->p_hi, v->p_lo, B, 3, H, W);
+  count_launch();
+  float *x = v->xa, *y = v->xb;
+  STK_TRY(vconv(c, "encoder.conv_in", v->p_hi, v->p_lo, H, W, x, nullptr));
+  int cin = ch;
+  for (int lvl = 0; lvl < 4; ++lvl) {
+    const int cout = ch * v->mult[lvl];
+    for (int b = 0; b < 2; ++b) {
+      STK_TRY(vresnet(c, "encoder.down." + std::to_string(lvl) + ".block." + std::to_string(b), x, y, H, W, cin, cout));
+      cin = cout;
+    }
+    if (lvl != 3) {
+      space_to_depth_planes_kernel<<<blocks_for((int64_t)B * H * W * (cin / 4), 256, 148 * 16), 256, 0, s>>>(x, v->p_hi, v->p_lo, B, H, W, cin);
+      count_launch();
+      H /= 2; W /= 2;
+      STK_TRY(vconv(c, "encoder.down." + std::to_string(lvl) + ".downsample.conv", v->p_hi, v->p_lo, H, W, y, nullptr, 2));
+      std::swap(x, y);
+    }
+  }
+  STK_TRY(vmid(c, "encoder", x, y, H, W, Cm));
+  STK_TRY(vnorm(c, "encoder.norm_out", x, (int64_t)H * W, Cm, true));
+  STK_TRY(vconv(c, "encoder.conv_out", v->p_hi, v->p_lo, H, W, v->out4, nullptr));       // [B, h, w, 32] = (mean | logvar)
+  nhwc_to_nchw_kernel<<<blocks_for((int64_t)B * 16 * H * W), 256, 0, s>>>(v->out4, mean_out_dev, B, H * W, 32, 0, 16);
+  count_launch();
+  if (logvar_out_dev) {
+    nhwc_to_nchw_kernel<<<blocks_for((int64_t)B * 16 * H * W), 256, 0, s>>>(v->out4, logvar_out_dev, B, H * W, 32, 16, 16);
+    count_launch();
+  }
   STK_CUDA(cudaGetLastError());
   return SELFTOK_OK;
 }

@@ -62,16 +62,34 @@ class SD3LatentFormat:
         return (latent / self.scale_factor) + self.shift_factor
 
 
-class DeviceVAE:
-    """`self.vae` with the call shape the pipeline uses (SelftokPipeline.py:215,288,316): `decode` runs on this repo's device VAE
-    decoder (csrc/vae.cu, fp32-faithful split-bf16 GEMMs), `encode` is delegated to `encoder_vae` (e.g. the diffusers
-    AutoencoderKL) -- the VAE encoder is not on the device yet.  `decoder_state_dict`: SDVAE keys, or diffusers keys
-    (`diffusers_keys=True`)."""
+class _LatentDist:
+    """What `vae.encode(x, return_dict=False)[0]` is to the pipeline (diffusers DiagonalGaussianDistribution): `.mode()` is the
+    call SelftokPipeline.encoding makes (:215); `.sample()` follows the same formula (logvar clamped to [-30, 20])."""
 
-    def __init__(self, decoder_state_dict, device, encoder_vae=None, diffusers_keys: bool = False):
+    def __init__(self, mean, logvar):
+        self.mean, self.logvar = mean, logvar.clamp(-30.0, 20.0)
+
+    def mode(self):
+        return self.mean
+
+    def sample(self, generator=None):
+        eps = torch.randn(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + torch.exp(0.5 * self.logvar) * eps
+
+
+class DeviceVAE:
+    """`self.vae` with the call shape the pipeline uses (SelftokPipeline.py:215,288,316) on this repo's device VAE (csrc/vae.cu,
+    fp32-faithful split-bf16 GEMMs): `decode` always; `encode` too when the state dict holds the encoder.* half and the images are
+    128 / 256 / 512 pixels square -- otherwise it is delegated to `encoder_vae` (e.g. the diffusers AutoencoderKL).
+    `state_dict`: SDVAE keys, or diffusers keys (`diffusers_keys=True`)."""
+
+    ENCODE_SIDES = (128, 256, 512)
+
+    def __init__(self, state_dict, device, encoder_vae=None, diffusers_keys: bool = False):
         from .capi import VaeDecoder
-        sd = VaeDecoder.from_diffusers_keys(decoder_state_dict) if diffusers_keys else decoder_state_dict
+        sd = VaeDecoder.from_diffusers_keys(state_dict) if diffusers_keys else state_dict
         self.decoder = VaeDecoder(sd, device=device)
+        self.has_encoder = any(k.startswith("encoder.") for k in sd)
         self.encoder_vae = encoder_vae
 
     def decode(self, z, return_dict=False):
@@ -79,8 +97,12 @@ class DeviceVAE:
         return (out,)
 
     def encode(self, x, return_dict=False):
+        if self.has_encoder and x.dim() == 4 and x.shape[2] == x.shape[3] and int(x.shape[2]) in self.ENCODE_SIDES:
+            mean, logvar = self.decoder.encode(x, return_logvar=True)
+            return (_LatentDist(mean.to(x.dtype), logvar.to(x.dtype)),)
         if self.encoder_vae is None:
-            raise SelftokError("DeviceVAE: no encoder (pass encoder_vae=..., e.g. diffusers.AutoencoderKL)")
+            raise SelftokError("DeviceVAE.encode: images must be 128/256/512 square with encoder.* weights loaded, or pass "
+                               "encoder_vae=... (e.g. diffusers.AutoencoderKL)")
         return self.encoder_vae.encode(x, return_dict=return_dict)
 
     def to(self, *a, **k):
@@ -99,7 +121,7 @@ def _load_vae(sd3_path, device, dtype):
     vae = AutoencoderKL.from_pretrained(sd3_path, subfolder="vae")
     vae.to(device).to(dtype)
     vae.eval()
-    # decode on this repo's device VAE, encode on the diffusers module
+    # both halves on this repo's device VAE; the diffusers module stays as the fallback for other image sizes
     return DeviceVAE(vae.state_dict(), device, encoder_vae=vae, diffusers_keys=True)
 
 

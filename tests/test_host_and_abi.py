@@ -152,12 +152,13 @@ def test_sharded_noise_and_row_gather_gloo_world2(tmp_path):
 
 def test_vae_key_mapping_from_diffusers_names():
     """The device VAE takes the in-tree SDVAE key names; a diffusers AutoencoderKL state dict is mapped onto them
-    (up_blocks listed lowest resolution first, attention projections stored as Linear)."""
+    (decoder up_blocks listed lowest resolution first, encoder down_blocks in order, attention projections stored as Linear)."""
     from selftoktokenizer_b200.capi import VaeDecoder
-    spec = synth.vae_state_dict_spec(128, encoder=False)
+    spec = synth.vae_state_dict_spec(128)
 
     def to_diffusers(name, shape):                      # the inverse renaming, written independently of the product code
-        n = name[len("decoder."):]
+        half = name[:len("decoder.")]
+        n = name[len(half):]
         n = n.replace("mid.block_1", "mid_block.resnets.0").replace("mid.block_2", "mid_block.resnets.1")
         n = n.replace("mid.attn_1.norm", "mid_block.attentions.0.group_norm").replace("mid.attn_1.q", "mid_block.attentions.0.to_q")
         n = n.replace("mid.attn_1.k", "mid_block.attentions.0.to_k").replace("mid.attn_1.v", "mid_block.attentions.0.to_v")
@@ -170,15 +171,21 @@ def test_vae_key_mapping_from_diffusers_names():
         m = re.match(r"up\.(\d)\.upsample\.(.*)", n)
         if m:
             n = f"up_blocks.{3 - int(m.group(1))}.upsamplers.0.{m.group(2)}"
+        m = re.match(r"down\.(\d)\.block\.(\d)\.(.*)", n)
+        if m:
+            n = f"down_blocks.{m.group(1)}.resnets.{m.group(2)}.{m.group(3)}"
+        m = re.match(r"down\.(\d)\.downsample\.(.*)", n)
+        if m:
+            n = f"down_blocks.{m.group(1)}.downsamplers.0.{m.group(2)}"
         if "attentions.0.to_" in n and n.endswith(".weight"):
             shape = shape[:2]                            # Linear [C, C] instead of a 1x1 conv
-        return "decoder." + n, shape
+        return half + n, shape
 
     fake = {}
     for name, (shape, _, _) in spec.items():
         dn, dshape = to_diffusers(name, tuple(shape))
         fake[dn] = torch.zeros(dshape)
-    fake["encoder.conv_in.weight"] = torch.zeros(1)      # ignored
+    fake["quant_conv.weight"] = torch.zeros(1)           # neither half: ignored
     back = VaeDecoder.from_diffusers_keys(fake)
     assert set(back) == set(spec)
     for name, (shape, _, _) in spec.items():

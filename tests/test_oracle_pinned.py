@@ -207,6 +207,19 @@ def test_vae_oracle_matches_reference_fixture(gold):
     assert np.abs(V.encode_moments(sd, x).numpy() - g["moments"]).max() < 2e-5
 
 
+def test_vae_oracle_encoder_matches_reference_at_full_width(gold):
+    """VAEEncoder at the shipped width (ch = 128) on 128 x 128 images: oracle/gen_golden.py vae_enc128 (the fixture the device
+    encoder is checked against in tests/test_parity_gpu.py)."""
+    import vae_oracle as V
+    g = gold("vae_enc128")
+    sd = synth.synth_vae_state_dict(ch=128)
+    x = synth.synth_tensor("golden.vae.x128", (2, 3, 128, 128), "emb", 0.5)
+    with torch.no_grad():
+        mom = V.encode_moments(sd, x).numpy()
+    assert mom.shape == (2, 32, 16, 16)
+    assert np.abs(mom - g["moments"]).max() < 5e-5
+
+
 def test_pixel_fixture_is_reference_latents_through_the_vae_oracle(gold):
     """tests/golden/tiny_pixels.npz == images_from_latents(reference pred_x0): the pixel end of SelftokPipeline.decoding
     (process_out -> vae.decode -> norm_ip, SelftokPipeline.py:284-294) restated in vae_oracle."""

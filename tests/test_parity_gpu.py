@@ -598,6 +598,73 @@ def test_device_vae_decoder_against_oracle(h, B):
     dec.close()
 
 
+def test_device_vae_encoder_against_reference_fixture(gold):
+    """f1, encode side: the SD3 VAE encoder on the device (stride-2 Downsample convolutions as polyphase implicit GEMMs) against
+    the REFERENCE's own VAEEncoder output on two seeded 128 x 128 images (tests/golden/vae_enc128.npz), and bit-reproducible."""
+    from selftoktokenizer_b200.capi import VaeDecoder
+    g = gold("vae_enc128")
+    vae = VaeDecoder(synth.synth_vae_state_dict(ch=128), device=DEV)
+    x = synth.synth_tensor("golden.vae.x128", (2, 3, 128, 128), "emb", 0.5)
+    mean, logvar = vae.encode(x, return_logvar=True)
+    mean2 = vae.encode(x)
+    mom = torch.cat([mean, logvar], dim=1).cpu().numpy()
+    err = float(np.abs(mom - g["moments"]).max())
+    print(f"device VAE encode 128x128 B=2: max-abs err vs the reference {err:.3e} (|moments|max {float(np.abs(g['moments']).max()):.2f})")
+    assert torch.equal(mean, mean2), "the device VAE must be bit-reproducible"
+    assert err < 2e-4
+    vae.close()
+
+
+@pytest.mark.parametrize("H,B", [(256, 2), (512, 1)])
+def test_device_vae_encoder_against_oracle(H, B):
+    """the same at the shipped image sizes against the pinned restatement (oracle/vae_oracle.py, fp32 on the host)."""
+    import vae_oracle as V
+    from selftoktokenizer_b200.capi import VaeDecoder
+    vsd = synth.synth_vae_state_dict(ch=128)
+    vae = VaeDecoder(vsd, device=DEV)
+    x = synth.synth_tensor(f"vae.dev.x{H}", (B, 3, H, H), "emb", 0.5)
+    mean, logvar = vae.encode(x, return_logvar=True)
+    with torch.no_grad():
+        ref = V.encode_moments(vsd, x)
+    err = float((torch.cat([mean, logvar], dim=1).cpu() - ref).abs().max())
+    print(f"device VAE encode {H}x{H} B={B}: max-abs err {err:.3e} (|moments|max {float(ref.abs().max()):.2f})")
+    assert err < 2e-4
+    # a decoder-only handle refuses to encode, loudly
+    dec_only = VaeDecoder(synth.synth_vae_state_dict(ch=128, encoder=False), device=DEV)
+    with pytest.raises(Exception):
+        dec_only.encode(x)
+    dec_only.close()
+    vae.close()
+
+
+def test_pixels_to_tokens_entirely_on_the_device(full_engine):
+    """SelftokPipeline.encoding with nothing left on the host: images -> device VAE encoder -> process_in -> Q-Former encoder -> VQ.
+    Against the oracle chain on the same images: the VAE latents agree to ~1e-5, so token ids may only differ where the
+    reference's own top-1 / top-2 cosine margin is at that rounding level."""
+    import vae_oracle as V
+    from selftoktokenizer_b200.pipeline import DeviceVAE, SD3LatentFormat
+    d = C.FULL
+    vsd = synth.synth_vae_state_dict(ch=128)
+    spec = synth.state_dict_spec(d)
+    sd = {n: synth.synth_tensor(n, sh, k, std) for n, (sh, k, std) in spec.items() if n.startswith("encoder.")}     # host copy for the oracle
+    img = synth.synth_tensor("full.images", (2, 3, 256, 256), "emb", 0.5)
+    vae = DeviceVAE(vsd, DEV)
+    lat = SD3LatentFormat().process_in(vae.encode(img.to(DEV), return_dict=False)[0].mode()).float()
+    with torch.no_grad():
+        lat_ref = V.latents_from_images(vsd, img)
+    lat_err = float((lat.cpu() - lat_ref).abs().max())
+    tok = full_engine.encode(lat).cpu().numpy()
+    with torch.no_grad():
+        _, tok_ref, z_ref = O.encode(sd, d, lat_ref)
+    margin = _top2_margin(sd, z_ref)
+    mism = tok != tok_ref.numpy()
+    print(f"pixels -> tokens on the device: latent max-abs err {lat_err:.3e}; {int(mism.sum())} / {mism.size} ids differ"
+          + (f", reference margins there {margin[mism]}" if mism.any() else ""))
+    assert lat_err < 2e-4
+    assert int(mism.sum()) <= 2 and (not mism.any() or float(margin[mism].max()) < 1e-4)
+    vae.decoder.close()
+
+
 def test_full_pixel_gate_on_device_vae(full_engine, gold):
     """The pixel-boundary parity gate with EVERYTHING after the tokens on the device: 50-step decode (B = 1, full geometry) ->
     process_out -> device VAE decoder -> norm_ip, against the reference's own pixels (tests/golden/full_pixels.npz)."""
