@@ -292,15 +292,21 @@ def run_extras(args, eng, dev, x0, noise, timed):
     # ---- f1: the SD3 VAE decoder on the device (what follows the token path in decoding()): latents -> pixels, batch 64
     try:
         from selftoktokenizer_b200.capi import VaeDecoder
-        dec = VaeDecoder(synth.synth_vae_state_dict(ch=128, encoder=False, device=dev), device=dev)
+        dec = VaeDecoder(synth.synth_vae_state_dict(ch=128, device=dev), device=dev)
         z = noise * 0.5
         dec.decode(z)
         msv, _ = timed(lambda: dec.decode(z, norm_ip=True) is None, 3)
         out["vae_decode"] = {"workload": f"batch={B} SD3 VAE decoder, 32x32x16 latents -> 256x256 pixels (split-bf16 tcgen05 implicit-GEMM convs)",
                              "value": B * 3 / (msv / 1000.0), "unit": UNIT, "ms_per_batch": msv / 3, "algorithmic_tflop_per_batch": 0.622 * B}
+        img = synth.synth_tensor("bench.images", (B, 3, 256, 256), "emb", 0.5, device=dev)
+        dec.encode(img)
+        mse, _ = timed(lambda: dec.encode(img) is None, 3)
+        out["vae_encode"] = {"workload": f"batch={B} SD3 VAE encoder, 256x256 pixels -> 32x32x16 latent means (stride-2 convs as polyphase implicit GEMMs)",
+                             "value": B * 3 / (mse / 1000.0), "unit": UNIT, "ms_per_batch": mse / 3, "algorithmic_tflop_per_batch": 0.273 * B}
         dec.close()
     except Exception as exc:  # noqa: BLE001 - the headline must not die on an auxiliary record
-        out["vae_decode"] = {"error": str(exc)[:200]}
+        out.setdefault("vae_decode", {"error": str(exc)[:200]})
+        out.setdefault("vae_encode", {"error": str(exc)[:200]})
     return out
 
 
