@@ -307,6 +307,36 @@ def run_extras(args, eng, dev, x0, noise, timed):
     except Exception as exc:  # noqa: BLE001 - the headline must not die on an auxiliary record
         out.setdefault("vae_decode", {"error": str(exc)[:200]})
         out.setdefault("vae_encode", {"error": str(exc)[:200]})
+    # ---- the reference's own user call at the PIXEL boundary: SelftokPipeline.encoding(images) -> tokens -> .decoding(tokens)
+    # -> images, host tensors in and out, both VAE halves + Q-Former + VQ + 50-step sampler on this library (BASELINE config 3)
+    try:
+        import contextlib
+        from selftoktokenizer_b200 import SelftokPipeline
+        from selftoktokenizer_b200.pipeline import DeviceVAE
+        vae = DeviceVAE(synth.synth_vae_state_dict(ch=128, device=dev), dev)
+        with contextlib.redirect_stdout(sys.stderr):                 # the class prints the reference's progress lines
+            pipe = SelftokPipeline(cfg=None, ckpt_path=None, sd3_path=None, datasize=256, device=dev, state_dict=synth.synth_state_dict(d, device=dev),
+                                   dims=d, vae=vae, precision=eng.precision)
+        img_h = synth.synth_tensor("bench.images", (B, 3, 256, 256), "emb", 0.5).clamp_(-1, 1).pin_memory()
+        res = {}
+
+        def pixel_step():
+            with contextlib.redirect_stdout(sys.stderr):
+                tok = pipe.encoding(img_h, dev).cpu().numpy()          # H2D of the images inside, D2H of the ids
+                res["img"] = pipe.decoding(tok, dev).cpu()             # host draw of the noise + H2D inside, D2H of the pixels
+        pixel_step()
+        msp, _ = timed(pixel_step, 2)
+        out["pixel_e2e"] = {"workload": f"batch={B}: SelftokPipeline.encoding(images [B,3,256,256] on the host) -> ids on the host -> "
+                                        "SelftokPipeline.decoding(ids) -> images on the host (VAE encoder + Q-Former + VQ + 50-step sampler + VAE "
+                                        "decoder, pipeline dtype bf16 as the reference's default)",
+                            "value": B * 2 / (msp / 1000.0), "unit": UNIT, "ms_per_batch": msp / 2,
+                            "h2d_bytes_per_step": int(img_h.numel() * 4 + B * d.K * 8 + noise.numel() * 4),
+                            "d2h_bytes_per_step": int(B * d.K * 8 + res["img"].numel() * res["img"].element_size()),
+                            "precision": pipe.engine.precision}
+        pipe.engine.close()
+        vae.decoder.close()
+    except Exception as exc:  # noqa: BLE001
+        out["pixel_e2e"] = {"error": str(exc)[:300]}
     return out
 
 
