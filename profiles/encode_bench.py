@@ -25,4 +25,7 @@ for _ in range(5):
     e1.record()
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-print("encode_b64_ms", sorted(ts)[len(ts) // 2], "tokens_checksum", int(tok.sum().item()))
+tok, _, feats = eng.encode(x0, return_aux=True)
+import hashlib
+print("encode_b64_ms", sorted(ts)[len(ts) // 2], "tokens_checksum", int(tok.sum().item()),
+      "features_sha1", hashlib.sha1(feats.cpu().numpy().tobytes()).hexdigest()[:16])
