@@ -190,3 +190,29 @@ def test_vae_key_mapping_from_diffusers_names():
     assert set(back) == set(spec)
     for name, (shape, _, _) in spec.items():
         assert tuple(back[name].shape) == tuple(shape), name
+
+
+def test_host_preprocessing_matches_torchvision():
+    """SURVEY 8f4 / the reference's test.py:27-31,45-47: Resize(data_size) + CenterCrop(data_size) + NormalizeToTensor on the way
+    in and save_image's quantisation on the way out, PIL-only here, bit-equal to torchvision where that is importable."""
+    from PIL import Image
+    from selftoktokenizer_b200.preprocess import load_images, resize_center_crop, to_uint8_hwc
+    rng = np.random.RandomState(0)
+    T = None
+    try:
+        import torchvision.transforms as T  # noqa: N812
+    except Exception:  # pragma: no cover
+        pass
+    for (w, h) in [(640, 480), (300, 517), (256, 256), (255, 1024), (1000, 256)]:
+        img = Image.fromarray(rng.randint(0, 256, (h, w, 3)).astype(np.uint8))
+        for size in (128, 256, 512):
+            mine = resize_center_crop(img, size)
+            assert mine.size == (size, size)
+            if T is not None:
+                ref = T.Compose([T.Resize(size), T.CenterCrop(size)])(img)
+                assert np.array_equal(np.array(ref), np.array(mine)), (w, h, size)
+    img = Image.fromarray(rng.randint(0, 256, (70, 90, 3)).astype(np.uint8))
+    x = load_images([img, img.convert("L")], 64)                      # grey input is promoted to 3 channels
+    assert tuple(x.shape) == (2, 3, 64, 64) and x.dtype == torch.float32 and float(x.min()) >= -1 and float(x.max()) <= 1
+    back = to_uint8_hwc((x[0] + 1) / 2)
+    assert np.array_equal(back, np.array(resize_center_crop(img, 64)))   # [-1,1] -> [0,1] -> uint8 is the identity on 8-bit pixels

@@ -6,6 +6,7 @@ cosine margin is below 1e-4, and is reported); reconstructed latents within 1e-3
 looser bound — it is NOT the parity mode.
 """
 import dataclasses
+import os
 
 import numpy as np
 import pytest
@@ -702,3 +703,21 @@ def test_caller_owned_workspace(tiny_engine, gold):
     # a larger batch than the block was sized for falls back to a library-owned block, transparently
     x5 = synth.synth_tensor("ws.x0", (5, d.in_channels, d.latent, d.latent), "emb", 1.0)
     assert tiny_engine.encode(x5).shape[0] == 5 and tiny_engine.device_bytes > base
+
+
+def test_roundtrip_driver_script(tmp_path):
+    """The reference's test.py on this library (python -m selftoktokenizer_b200.roundtrip): image file -> tokens .npy -> image
+    file, shipped 256 / 512-token YAML, seeded synthetic checkpoints (--synthetic), everything incl. both VAE halves on the device."""
+    from PIL import Image
+    from selftoktokenizer_b200 import roundtrip
+    rng = np.random.RandomState(1)
+    src = tmp_path / "in.png"
+    Image.fromarray(rng.randint(0, 256, (300, 400, 3)).astype(np.uint8)).save(src)
+    yml = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "configs", "selftok_256_512tok.yml")
+    rc = roundtrip.main(["--yml-path", yml, "--synthetic", "--images", str(src), "--tokens", str(tmp_path / "token.npy"),
+                         "--out-prefix", str(tmp_path / "re"), "--device", DEV])
+    assert rc == 0
+    tok = np.load(tmp_path / "token.npy")
+    assert tok.shape == (1, 512) and tok.dtype == np.int64 and tok.min() >= 0 and tok.max() < 32768
+    out = np.array(Image.open(tmp_path / "re_0_256.png"))
+    assert out.shape == (256, 256, 3) and out.dtype == np.uint8 and out.std() > 0
