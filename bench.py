@@ -253,6 +253,15 @@ def run_extras(args, eng, dev, x0, noise, timed):
                       "bound": "fp32 FFMA pipe (35.5 GFLOP on 71.6 MB: 11 us of HBM time); the HBM fraction is reported because the "
                                "north-star asks for it (SURVEY 8d)", "timing": "median of 10, CUDA events, L2 flushed"}}
     del flush
+    # ---- serving view of the headline: ONE image through encode + 50-step decode (config 1's shape on the GPU)
+    x1, n1 = x0[:1].contiguous(), noise[:1].contiguous()
+
+    def one_image():
+        eng.decode(eng.encode(x1), n1)
+    one_image()
+    ms1, _ = timed(one_image, 3)
+    out["batch1_latency"] = {"workload": "batch=1 256x256 encode + 50-step decode (one CUDA-graph replay per call), device buffers",
+                             "value": ms1 / 3, "unit": "ms", "higher_is_better": False, "images_per_s": 3000.0 / ms1}
     # ---- config 3 in the fp32-faithful mode
     if args.precision != "bf16x3":
         e3 = Engine(d, synth.synth_state_dict(d, device=dev), device=dev, precision="bf16x3", steps=DECODE_STEPS)

@@ -32,6 +32,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace stk {
 
@@ -620,7 +621,10 @@ int launch_attention_tc5(const __nv_bfloat16* qkv16, int B, int S, int H, int ct
     dim3 grid(std::min(n_items, A5<3>::MIN_CTAS * g_num_sms));
     attention_tc5_kernel<false, 3><<<grid, NUM_THREADS, A5<3>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
   } else {
-    dim3 grid(std::min(n_items, 2 * g_num_sms));                     // persistent: two CTAs per SM walk the item list
+    // persistent: two CTAs per SM walk the item list.  SELFTOK_ATTN5_CTAS_PER_SM=1 is a measurement knob (how much a CTA is
+    // slowed by its co-resident twin: profiles/r2_attention_investigation.md); it never changes results.
+    static const int ctas_per_sm = [] { const char* e = getenv("SELFTOK_ATTN5_CTAS_PER_SM"); return (e && e[0] == '1') ? 1 : 2; }();
+    dim3 grid(std::min(n_items, ctas_per_sm * g_num_sms));
     if (fp16) attention_tc5_kernel<true, 1><<<grid, NUM_THREADS, A5<1>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
     else attention_tc5_kernel<false, 1><<<grid, NUM_THREADS, A5<1>::SMEM_BYTES, s>>>(mq, mkv, mql, mkvl, p);
   }
