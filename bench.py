@@ -56,6 +56,37 @@ def peaks():
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def other_class_rooflines(prof, B, precision, pk):
+    """BASELINE's '% of roofline per kernel class' for the classes that are not the dominant one: algorithmic work of the profiled
+    encode + 50-step decode divided by the class's event-timed total (same pass as `roofline`)."""
+    d = C.FULL
+    tb = S.make_tables(d.K, d.stages, d.k_per_stage, DECODE_STEPS)
+    D, N, L = d.dit_hidden, d.n_img, d.dit_depth
+    attn_flops = ln_bytes = 0.0
+    plane = 4 if precision == "bf16x3" else 2                       # 16-bit hi (+ lo) operand planes written per element
+    for i in range(DECODE_STEPS):
+        kc = int(tb.k[i]) + 1
+        Sj = kc + N
+        attn_flops += L * 4.0 * Sj * Sj * D * B                      # Q K^T + P V over the joint sequence, every row sees every key
+        ln_bytes += (2 * L * N + (2 * L - 1) * kc + N) * B * D * (4 + plane)   # x fp32 in, planes out; last ctx block pre_only; final LN
+    out = {}
+    if "attention" in prof and prof["attention"][0] > 0:
+        ach = attn_flops / (prof["attention"][0] / 1000.0) / 1e12
+        out["attention"] = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+                            "note": "head dim 64: latency-chain bound, see profiles/r2_attention_investigation.md"}
+    if "ln_modulate" in prof and prof["ln_modulate"][0] > 0:
+        ach = ln_bytes / (prof["ln_modulate"][0] / 1000.0) / 1e9
+        out["ln_modulate"] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                              "note": "fp32 residual stream in, 16-bit operand planes out; the adaLN tables are L2-resident"}
+    if "linear_f32" in prof and prof["linear_f32"][0] > 0:
+        enc_flops = 65.6e9 * B                                       # DESIGN.md section 4: encoder GEMMs per image
+        ach = enc_flops / (prof["linear_f32"][0] / 1000.0) / 1e12
+        peak = 148 * 128 * 2 * 1.965e9 / 1e12
+        out["linear_f32"] = {"bound": "fp32 FFMA", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                             "note": "Q-Former encoder, fp32 for bit-exact ids; peak = 148 SMs x 128 lanes x 2 x 1.965 GHz (nominal)"}
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -427,6 +458,7 @@ def run_gpu(args):
     d2h = tok_h.numel() * 8 + out_h.numel() * 4
     # ---- roofline of the dominant kernel class: one profiled (graph-off, event-bracketed) step
     roof = None
+    class_roof = None
     prof = {}
     if rank == 0:
         eng.set_use_graph(False)
@@ -452,6 +484,7 @@ def run_gpu(args):
                     "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,
                     "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs)"}
+        class_roof = other_class_rooflines(prof, B, args.precision, pk)
     # ---- the other BASELINE configs, measured in the same run (N = 1 only; each engine is built, timed and released)
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:
@@ -481,6 +514,7 @@ def run_gpu(args):
                         "ms_per_step": ms_h / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "extra": extra,
                 "kernel_classes_ms": {k: round(v[0], 3) for k, v in prof.items()},
+                "kernel_classes_roofline": class_roof,
                 "kernel_classes_launches": {k: v[1] for k, v in prof.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:
