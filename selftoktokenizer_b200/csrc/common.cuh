@@ -155,4 +155,23 @@ __device__ __forceinline__ uint32_t pack2_resid_bf16(float a, float b, uint32_t 
   return r;
 }
 
+// packed fp32 pipe (Blackwell FFMA2 / FADD2: one issue slot for two lanes of arithmetic): (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void ffma2(float a0, float a1, float b0, float b1, float c0, float c1, float& d0, float& d1) {
+  asm("{\n\t.reg .b64 a, b, c;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "mov.b64 c, {%6, %7};\n\t"
+      "fma.rn.f32x2 a, a, b, c;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float a0, float a1, float b0, float b1, float& d0, float& d1) {
+  asm("{\n\t.reg .b64 a, b;\n\t"
+      "mov.b64 a, {%2, %3};\n\t"
+      "mov.b64 b, {%4, %5};\n\t"
+      "add.rn.f32x2 a, a, b;\n\t"
+      "mov.b64 {%0, %1}, a;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 }  // namespace stk
