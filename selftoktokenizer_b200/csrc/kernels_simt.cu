@@ -290,8 +290,10 @@ struct LnPairParams {
   float eps;
 };
 
-// FULL: D == MAXV * 128 exactly (1536 with MAXV 12: the MMDiT), so that no per-chunk bounds predicate is compiled in
-template <int MAXV, bool FP16, bool LO, bool FULL>
+// FULL: D == MAXV * 128 exactly (1536 with MAXV 12: the MMDiT), so that no per-chunk bounds predicate is compiled in.
+// ROWS: rows per warp (the CTA covers 8 * ROWS rows that share one table row): the prologue -- index arithmetic, the staged table,
+// the CTA launch itself -- is ~370 of the ~590 instructions a warp spends on its first row.
+template <int MAXV, bool FP16, bool LO, bool FULL, int ROWS>
 __global__ void __launch_bounds__(256) ln_mod_pair_kernel(const LnPairParams p) {
   __shared__ __align__(16) float4 tab[2 * MAXV * 32];
   const bool second = (int)blockIdx.x >= p.nblk0;
@@ -299,18 +301,12 @@ __global__ void __launch_bounds__(256) ln_mod_pair_kernel(const LnPairParams p) 
   const int blk = second ? (int)blockIdx.x - p.nblk0 : (int)blockIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nv = p.D >> 2;
-  int64_t m, trow;
-  bool active;
-  if (q.imgs > 0) {                                    // position-major: row = img * period + pos
-    const int64_t img = (int64_t)(blk / q.period) * 8 + wid;
-    active = img < q.imgs;
-    trow = blk % q.period;
-    m = img * q.period + trow;
-  } else {                                             // natural order, one table row for the whole problem
-    m = (int64_t)blk * 8 + wid;
-    active = m < q.M;
-    trow = 0;
-  }
+  // row r of this warp: position-major (imgs > 0): image (blk / period) * 8 ROWS + wid + 8 r at position blk % period;
+  // natural order: row blk * 8 ROWS + wid + 8 r, one table row for the whole problem
+  const bool pos_major = q.imgs > 0;
+  const int64_t first = pos_major ? (int64_t)(blk / q.period) * (8 * ROWS) + wid : (int64_t)blk * (8 * ROWS) + wid;
+  const int64_t trow = pos_major ? blk % q.period : 0;
+  const int64_t limit = pos_major ? q.imgs : q.M;
   {
     const float4* sh = reinterpret_cast<const float4*>(q.shift + trow * q.ld_mod);
     const float4* sc = reinterpret_cast<const float4*>(q.scale + trow * q.ld_mod);
@@ -321,57 +317,68 @@ __global__ void __launch_bounds__(256) ln_mod_pair_kernel(const LnPairParams p) 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  const float4* xr = reinterpret_cast<const float4*>(q.x + (active ? m : 0) * (int64_t)p.D);
   // All row arithmetic runs on the packed fp32 pipe (FADD2 / FFMA2, two elements per issue slot): under the 1 kW cap the SMs
   // clock at ~1.35 GHz and this kernel is bound by instruction issue, not by HBM (91 % of the copy rate at burst clocks,
   // 69 % in situ before this change).
-  float4 v[MAXV];
-  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 1
+  for (int r = 0; r < ROWS; ++r) {
+    const int64_t unit = first + 8 * r;
+    const bool active = unit < limit;                                  // warp-uniform
+    const int64_t m = pos_major ? unit * q.period + trow : unit;
+    float4 v[MAXV];
+    float rstd = 0.f, nmr = 0.f;
+    if (active) {
+      const float4* xr = reinterpret_cast<const float4*>(q.x + m * (int64_t)p.D);
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + i * 32;
-    if (FULL || idx < nv) {
-      v[i] = __ldcs(xr + idx);
-      fadd2(s0, s1, v[i].x, v[i].y, s0, s1);
-      fadd2(s0, s1, v[i].z, v[i].w, s0, s1);
+      for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (FULL || idx < nv) {
+          v[i] = __ldcs(xr + idx);
+          fadd2(s0, s1, v[i].x, v[i].y, s0, s1);
+          fadd2(s0, s1, v[i].z, v[i].w, s0, s1);
+        }
+      }
+      const float mean = warp_sum(s0 + s1) / (float)p.D;
+      const float nmean = -mean;
+      float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int idx = lane + i * 32;
+        if (FULL || idx < nv) {
+          float a, b, c, d;
+          fadd2(v[i].x, v[i].y, nmean, nmean, a, b);
+          fadd2(v[i].z, v[i].w, nmean, nmean, c, d);
+          ffma2(a, b, a, b, q0, q1, q0, q1);
+          ffma2(c, d, c, d, q0, q1, q0, q1);
+        }
+      }
+      rstd = rsqrtf(warp_sum(q0 + q1) / (float)p.D + p.eps);
+      nmr = nmean * rstd;                                              // xn = x * rstd - mean * rstd
     }
-  }
-  const float mean = warp_sum(s0 + s1) / (float)p.D;
-  const float nmean = -mean;
-  float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + i * 32;
-    if (FULL || idx < nv) {
-      float a, b, c, d;
-      fadd2(v[i].x, v[i].y, nmean, nmean, a, b);
-      fadd2(v[i].z, v[i].w, nmean, nmean, c, d);
-      ffma2(a, b, a, b, q0, q1, q0, q1);
-      ffma2(c, d, c, d, q0, q1, q0, q1);
+    if (r == 0) {                                                      // the table is needed from here on; every warp passes once
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q0 + q1) / (float)p.D + p.eps);
-  const float nmr = nmean * rstd;                                    // xn = x * rstd - mean * rstd
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (!active) return;
-  uint2* oh = reinterpret_cast<uint2*>(q.out_hi + m * (int64_t)p.D);
-  uint2* ol = LO ? reinterpret_cast<uint2*>(q.out_lo + m * (int64_t)p.D) : nullptr;
+    if (!active) continue;
+    uint2* oh = reinterpret_cast<uint2*>(q.out_hi + m * (int64_t)p.D);
+    uint2* ol = LO ? reinterpret_cast<uint2*>(q.out_lo + m * (int64_t)p.D) : nullptr;
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + i * 32;
-    if (FULL || idx < nv) {
-      const float4 h4 = tab[idx], s4 = tab[MAXV * 32 + idx];
-      float4 y, g;
-      ffma2(v[i].x, v[i].y, rstd, rstd, nmr, nmr, y.x, y.y);
-      ffma2(v[i].z, v[i].w, rstd, rstd, nmr, nmr, y.z, y.w);
-      fadd2(s4.x, s4.y, 1.f, 1.f, g.x, g.y);
-      fadd2(s4.z, s4.w, 1.f, 1.f, g.z, g.w);
-      ffma2(y.x, y.y, g.x, g.y, h4.x, h4.y, y.x, y.y);
-      ffma2(y.z, y.w, g.z, g.w, h4.z, h4.w, y.z, y.w);
-      const uint32_t p0 = pack2_sat16(y.x, y.y, FP16), p1 = pack2_sat16(y.z, y.w, FP16);
-      oh[idx] = make_uint2(p0, p1);
-      if (LO) ol[idx] = make_uint2(pack2_resid_bf16(y.x, y.y, p0), pack2_resid_bf16(y.z, y.w, p1));
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (FULL || idx < nv) {
+        const float4 h4 = tab[idx], s4 = tab[MAXV * 32 + idx];
+        float4 y, g;
+        ffma2(v[i].x, v[i].y, rstd, rstd, nmr, nmr, y.x, y.y);
+        ffma2(v[i].z, v[i].w, rstd, rstd, nmr, nmr, y.z, y.w);
+        fadd2(s4.x, s4.y, 1.f, 1.f, g.x, g.y);
+        fadd2(s4.z, s4.w, 1.f, 1.f, g.z, g.w);
+        ffma2(y.x, y.y, g.x, g.y, h4.x, h4.y, y.x, y.y);
+        ffma2(y.z, y.w, g.z, g.w, h4.z, h4.w, y.z, y.w);
+        const uint32_t p0 = pack2_sat16(y.x, y.y, FP16), p1 = pack2_sat16(y.z, y.w, FP16);
+        oh[idx] = make_uint2(p0, p1);
+        if (LO) ol[idx] = make_uint2(pack2_resid_bf16(y.x, y.y, p0), pack2_resid_bf16(y.z, y.w, p1));
+      }
     }
   }
 }
@@ -382,6 +389,17 @@ int launch_ln_mod_pair(const LnProblem* probs, int n, int D, float eps, cudaStre
   p.D = D; p.eps = eps;
   int nblk[2] = {0, 0};
   bool lo = false;
+  // two rows per warp when that still leaves >= 4 CTAs per SM of a B200 (halves the per-row share of the prologue); else one
+  auto ctas_for = [&](int rows_per_warp) {
+    int64_t c = 0;
+    for (int i = 0; i < n; ++i) {
+      const LnProblem& q = probs[i];
+      const int64_t units = q.period > 1 ? q.M / q.period : q.M;
+      c += (q.period > 1 ? q.period : 1) * ((units + 8 * rows_per_warp - 1) / (8 * rows_per_warp));
+    }
+    return c;
+  };
+  const int rows = ctas_for(2) >= 4 * 148 ? 2 : 1;
   for (int i = 0; i < 2; ++i) {
     if (i >= n) { p.pr[i] = probs[0]; p.pr[i].M = 0; continue; }
     LnProblem q = probs[i];
@@ -391,30 +409,35 @@ int launch_ln_mod_pair(const LnProblem* probs, int n, int D, float eps, cudaStre
     if (q.period > 1) {                                // per-position table: position-major, needs whole images
       STK_CHECK(q.M % q.period == 0, -1, "ln_mod_pair: rows must be whole images of `period` positions");
       q.imgs = (int)(q.M / q.period);
-      nblk[i] = q.period * ((q.imgs + 7) / 8);
+      nblk[i] = q.period * ((q.imgs + 8 * rows - 1) / (8 * rows));
     } else {
       q.period = 1; q.imgs = 0;
-      nblk[i] = (int)((q.M + 7) / 8);
+      nblk[i] = (int)((q.M + 8 * rows - 1) / (8 * rows));
     }
     p.pr[i] = q;
   }
   STK_CHECK(!(fp16 && lo), -1, "ln_mod_pair: the fp16 mode has no residual planes");
   p.nblk0 = nblk[0];
   const unsigned grid = (unsigned)(nblk[0] + nblk[1]);
+#define STK_LNP3(MAXV, FULL, ROWS)                                                          \
+  do {                                                                                      \
+    if (fp16) ln_mod_pair_kernel<MAXV, true, false, FULL, ROWS><<<grid, 256, 0, s>>>(p);    \
+    else if (lo) ln_mod_pair_kernel<MAXV, false, true, FULL, ROWS><<<grid, 256, 0, s>>>(p); \
+    else ln_mod_pair_kernel<MAXV, false, false, FULL, ROWS><<<grid, 256, 0, s>>>(p);        \
+  } while (0)
 #define STK_LNP(MAXV)                                                                       \
   do {                                                                                      \
     if (D == MAXV * 128) {                                                                  \
-      if (fp16) ln_mod_pair_kernel<MAXV, true, false, true><<<grid, 256, 0, s>>>(p);        \
-      else if (lo) ln_mod_pair_kernel<MAXV, false, true, true><<<grid, 256, 0, s>>>(p);     \
-      else ln_mod_pair_kernel<MAXV, false, false, true><<<grid, 256, 0, s>>>(p);            \
-    } else if (fp16) ln_mod_pair_kernel<MAXV, true, false, false><<<grid, 256, 0, s>>>(p);  \
-    else if (lo) ln_mod_pair_kernel<MAXV, false, true, false><<<grid, 256, 0, s>>>(p);      \
-    else ln_mod_pair_kernel<MAXV, false, false, false><<<grid, 256, 0, s>>>(p);             \
+      if (rows == 2) STK_LNP3(MAXV, true, 2); else STK_LNP3(MAXV, true, 1);                 \
+    } else {                                                                                \
+      if (rows == 2) STK_LNP3(MAXV, false, 2); else STK_LNP3(MAXV, false, 1);               \
+    }                                                                                       \
   } while (0)
   if (D <= 512) STK_LNP(4);
   else if (D <= 1536) STK_LNP(12);
   else STK_LNP(16);
 #undef STK_LNP
+#undef STK_LNP3
   count_launch();
   STK_CUDA(cudaGetLastError());
   return 0;
