@@ -66,11 +66,14 @@ __global__ void __launch_bounds__(256, 2) linear_f32_kernel(const LinParams p) {
       Ws[buf][kq + 0][r] = rw[i].x; Ws[buf][kq + 1][r] = rw[i].y; Ws[buf][kq + 2][r] = rw[i].z; Ws[buf][kq + 3][r] = rw[i].w;
     }
   };
-  float acc[TM][TN];
+  // accumulators as packed pairs (acc[i][2 j2], acc[i][2 j2 + 1]): the inner product runs on FFMA2 (fma.rn.f32x2: two independent
+  // round-to-nearest FMAs per issue slot, bit-identical to fmaf per element, same k order), which leaves every other issue slot
+  // to the shared-memory loads -- the scalar version spent all of them on FFMA and sat at half the FMA-pipe rate
+  unsigned long long acc2[TM][TN / 2];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TN / 2; ++j) acc2[i][j] = 0ull;
 
   const int nk = (p.K + BK - 1) / BK;
   gload(0);
@@ -81,7 +84,8 @@ __global__ void __launch_bounds__(256, 2) linear_f32_kernel(const LinParams p) {
     if (kb + 1 < nk) gload((kb + 1) * BK);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      float a[TM], w[TN];
+      float a[TM];
+      unsigned long long w2[TN / 2];
 #pragma unroll
       for (int c = 0; c < CM; ++c) {
         float4 v = *reinterpret_cast<const float4*>(&As[buf][k][c * (BM / CM) + ty * 4]);
@@ -89,13 +93,16 @@ __global__ void __launch_bounds__(256, 2) linear_f32_kernel(const LinParams p) {
       }
 #pragma unroll
       for (int c = 0; c < CN; ++c) {
-        float4 v = *reinterpret_cast<const float4*>(&Ws[buf][k][c * (BN / CN) + tx * 4]);
-        w[c * 4 + 0] = v.x; w[c * 4 + 1] = v.y; w[c * 4 + 2] = v.z; w[c * 4 + 3] = v.w;
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(&Ws[buf][k][c * (BN / CN) + tx * 4]);
+        w2[c * 2 + 0] = v.x; w2[c * 2 + 1] = v.y;
       }
 #pragma unroll
-      for (int i = 0; i < TM; ++i)
+      for (int i = 0; i < TM; ++i) {
+        unsigned long long ad;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(ad) : "f"(a[i]));
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        for (int j = 0; j < TN / 2; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(ad), "l"(w2[j]));
+      }
     }
     if (kb + 1 < nk) {
       sstore(buf ^ 1);
@@ -117,7 +124,8 @@ __global__ void __launch_bounds__(256, 2) linear_f32_kernel(const LinParams p) {
       for (int j = 0; j < 4; ++j) {
         const int nn = n + j;
         if (nn >= p.N) continue;
-        float y = acc[i][c * 4 + j];
+        const unsigned long long pr = acc2[i][c * 2 + (j >> 1)];
+        float y = __uint_as_float((j & 1) ? (uint32_t)(pr >> 32) : (uint32_t)pr);
         if (e.bias) y += e.bias[nn];
         y = apply_act(y, e.act);
         if (e.mode == EPI_STORE) {
