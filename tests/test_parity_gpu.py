@@ -721,3 +721,41 @@ def test_roundtrip_driver_script(tmp_path):
     assert tok.shape == (1, 512) and tok.dtype == np.int64 and tok.min() >= 0 and tok.max() < 32768
     out = np.array(Image.open(tmp_path / "re_0_256.png"))
     assert out.shape == (256, 256, 3) and out.dtype == np.uint8 and out.std() > 0
+
+
+def test_two_handles_on_two_host_threads(tiny_sd, gold):
+    """SURVEY 8b threading: the reference is single-threaded; the C ABI promises more -- one handle per host thread, each on its
+    own stream (graph capture is thread-local, the launch counter and last-error are thread-local): two engines driven
+    concurrently give bit-identical results to the sequential runs."""
+    import threading
+    from selftoktokenizer_b200.capi import Engine
+    g = gold("tiny")
+    d = C.TINY
+    tok, noise = torch.from_numpy(g["tokens"]), torch.from_numpy(g["noise"])
+    x0 = synth.synth_tensor("golden.tiny.x0", (3, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    engines = [Engine(d, tiny_sd, device=DEV, precision=p) for p in ("fp16", "bf16x3")]
+    ref = [(e.encode(x0).cpu(), e.decode(tok, noise).cpu()) for e in engines]
+    out, err = [None, None], []
+
+    def work(i):
+        try:
+            st = torch.cuda.Stream(device=DEV)
+            with torch.cuda.stream(st):
+                for _ in range(4):
+                    t = engines[i].encode(x0)
+                    x = engines[i].decode(tok, noise)
+                st.synchronize()
+                out[i] = (t.cpu(), x.cpu())
+        except Exception as exc:  # noqa: BLE001
+            err.append(exc)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not err, err
+    for i in range(2):
+        assert torch.equal(out[i][0], ref[i][0]) and torch.equal(out[i][1], ref[i][1]), f"engine {i} changed under concurrency"
+    for e in engines:
+        e.close()
