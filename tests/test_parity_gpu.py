@@ -759,3 +759,21 @@ def test_two_handles_on_two_host_threads(tiny_sd, gold):
         assert torch.equal(out[i][0], ref[i][0]) and torch.equal(out[i][1], ref[i][1]), f"engine {i} changed under concurrency"
     for e in engines:
         e.close()
+
+
+def test_large_batch_is_bitwise_shard_invariant(full_engine):
+    """per-image arithmetic must not depend on the batch size or on the position inside the batch.  Batch 80 (not a
+    multiple of the bench's 64; 61 440 joint rows, every index path beyond its bench range) against batch 4: ids and 50-step
+    latents of the shared images are bit-identical."""
+    d = C.FULL
+    x0 = synth.synth_tensor("bench.x0.0", (80, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    noise = synth.synth_tensor("bench.noise.0", (80, d.in_channels, d.latent, d.latent), "emb", 1.0)
+    tok80 = full_engine.encode(x0)
+    x80 = full_engine.decode(tok80, noise, steps=6)
+    tok4 = full_engine.encode(x0[:4])
+    x4 = full_engine.decode(tok4, noise[:4], steps=6)
+    tail = full_engine.decode(tok80[76:], noise[76:], steps=6)
+    assert torch.equal(tok80[:4].cpu(), tok4.cpu())
+    assert torch.equal(x80[:4].cpu(), x4.cpu()), float((x80[:4] - x4).abs().max())
+    assert torch.equal(x80[76:].cpu(), tail.cpu())
+    assert torch.isfinite(x80).all()
