@@ -518,20 +518,33 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnParams p) 
     }
     __syncthreads();
     // ---- S = Q K^T (4 x 4 per thread)
+    // packed fp32 pipe (FFMA2: two independent round-to-nearest FMAs per issue slot, bit-identical to fmaf per element and in the
+    // same d order): accumulators as key pairs, the query element duplicated into both lanes
     float sacc[4][4];
+    {
+      unsigned long long s2[4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+      for (int i = 0; i < 4; ++i) s2[i][0] = s2[i][1] = 0ull;
 #pragma unroll 8
-    for (int d = 0; d < HD; ++d) {
-      float4 a = *reinterpret_cast<const float4*>(&Qt[d * (BQ + 4) + ty * 4]);
-      float4 kk = *reinterpret_cast<const float4*>(&Kt[d * (BKV + 4) + tx * 4]);
-      float av[4] = {a.x, a.y, a.z, a.w}, kv[4] = {kk.x, kk.y, kk.z, kk.w};
+      for (int d = 0; d < HD; ++d) {
+        const float4 a = *reinterpret_cast<const float4*>(&Qt[d * (BQ + 4) + ty * 4]);
+        const ulonglong2 kk = *reinterpret_cast<const ulonglong2*>(&Kt[d * (BKV + 4) + tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unsigned long long ad;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(ad) : "f"(av[i]));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(s2[i][0]) : "l"(ad), "l"(kk.x));
+          asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(s2[i][1]) : "l"(ad), "l"(kk.y));
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) sacc[i][j] = fmaf(av[i], kv[j], sacc[i][j]);
+        for (int j = 0; j < 2; ++j) {
+          sacc[i][2 * j] = __uint_as_float((uint32_t)s2[i][j]);
+          sacc[i][2 * j + 1] = __uint_as_float((uint32_t)(s2[i][j] >> 32));
+        }
     }
     // ---- online softmax over this tile (row statistics shared by the 16 threads of a half-warp)
 #pragma unroll
@@ -565,17 +578,48 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnParams p) 
     }
     __syncthreads();
     // ---- O += P V
-#pragma unroll 8
-    for (int key = 0; key < BKV; ++key) {
-      float4 pp = *reinterpret_cast<const float4*>(&Pt[key * (BQ + 4) + ty * 4]);
-      float pr[4] = {pp.x, pp.y, pp.z, pp.w};
-      float vv[DV];
-#pragma unroll
-      for (int d = 0; d < DV; ++d) vv[d] = Vs[key * HD + tx * DV + d];
+    if (DV % 2 == 0) {                                     // head dims 32 / 64: output-dim pairs on FFMA2, P duplicated
+      constexpr int DP = DV / 2 > 0 ? DV / 2 : 1;
+      unsigned long long o2[4][DP];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int d = 0; d < DV; ++d) o[i][d] = fmaf(pr[i], vv[d], o[i][d]);
+        for (int d = 0; d < DP; ++d) asm("mov.b64 %0, {%1, %2};" : "=l"(o2[i][d]) : "f"(o[i][2 * d]), "f"(o[i][(2 * d + 1) % DV]));
+#pragma unroll 8
+      for (int key = 0; key < BKV; ++key) {
+        const float4 pp = *reinterpret_cast<const float4*>(&Pt[key * (BQ + 4) + ty * 4]);
+        const float pr[4] = {pp.x, pp.y, pp.z, pp.w};
+        unsigned long long v2[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) v2[d] = *reinterpret_cast<const unsigned long long*>(&Vs[key * HD + tx * DV + 2 * d]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          unsigned long long pd;
+          asm("mov.b64 %0, {%1, %1};" : "=l"(pd) : "f"(pr[i]));
+#pragma unroll
+          for (int d = 0; d < DP; ++d) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o2[i][d]) : "l"(pd), "l"(v2[d]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+          o[i][2 * d] = __uint_as_float((uint32_t)o2[i][d]);
+          if (2 * d + 1 < DV) o[i][2 * d + 1] = __uint_as_float((uint32_t)(o2[i][d] >> 32));
+        }
+    } else {
+#pragma unroll 8
+      for (int key = 0; key < BKV; ++key) {
+        float4 pp = *reinterpret_cast<const float4*>(&Pt[key * (BQ + 4) + ty * 4]);
+        float pr[4] = {pp.x, pp.y, pp.z, pp.w};
+        float vv[DV];
+#pragma unroll
+        for (int d = 0; d < DV; ++d) vv[d] = Vs[key * HD + tx * DV + d];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int d = 0; d < DV; ++d) o[i][d] = fmaf(pr[i], vv[d], o[i][d]);
+      }
     }
   }
   // ---- normalise + store
