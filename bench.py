@@ -483,7 +483,8 @@ def run_gpu(args):
                                 "one CUDA graph; class shares of the two agree within 1 %)",
                     "peak_source": pk["source"], "launches": g_n, "avg_launch_ms": g_ms / g_n,
                     "algorithmic_flops_per_launch": flops / g_n, "share_of_step": g_ms / total_ms,
-                    "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs)"}
+                    "note": "FLOPs counted once per product (the bf16x3 split passes are overhead, not useful FLOPs); the peak is the bf16 cuBLAS "
+                            "figure -- IEEE-half operands draw more power per MMA, the same GEMMs on bf16 operands run 4.8 % faster at the 1 kW cap"}
         class_roof = other_class_rooflines(prof, B, args.precision, pk)
     # ---- the other BASELINE configs, measured in the same run (N = 1 only; each engine is built, timed and released)
     extra = None
