@@ -107,6 +107,7 @@ struct selftok_engine {
   void* user_ws[2] = {nullptr, nullptr};          // caller-provided workspaces (selftok_set_workspace): [0] encode, [1] decode / render
   size_t user_ws_bytes[2] = {0, 0};
   std::map<std::pair<int, int>, std::pair<cudaGraphExec_t, int64_t>> graphs;   // (B, steps) -> (exec, launches)
+  std::map<int, std::pair<cudaGraphExec_t, int64_t>> enc_graphs;               // encode, B -> (exec, launches)
   int64_t last_launches = 0;
   // optional per-kernel-class timing (CUDA events around every launch; only meaningful with graphs disabled)
   bool prof_on = false;
@@ -264,6 +265,8 @@ static void free_dws(selftok_engine* e) {
   e->dws = DecodeWs();
 }
 static void free_ews(selftok_engine* e) {
+  for (auto& g : e->enc_graphs) cudaGraphExecDestroy(g.second.first);         // graphs hold pointers into the workspace
+  e->enc_graphs.clear();
   if (e->ews.own) { cudaFree(e->ews.own); e->bytes -= (int64_t)e->ews.own_bytes; }
   e->ews = EncodeWs();
 }
@@ -783,11 +786,48 @@ extern "C" __attribute__((visibility("default"))) int selftok_encode(selftok_han
   HOT_PROLOGUE(e);
   STK_CHECK(x0_dev && tokens_dev && B > 0, SELFTOK_ERR_BAD_ARG, "selftok_encode: bad argument");
   STK_TRY(ensure_ews(e, B));
-  STK_TRY(encoder_features(e, x0_dev, B, s));
   const int64_t R = (int64_t)B * e->cfg.K;
-  STK_TRY(run_vq(e, e->ews.q, R, tokens_dev, outs_q_dev ? outs_q_dev : e->ews.outs_q, s));
-  if (feats_dev) STK_CUDA(cudaMemcpyAsync(feats_dev, e->ews.q, sizeof(float) * R * e->cfg.enc_qdim, cudaMemcpyDeviceToDevice, s));
-  e->last_launches = g_launch_count - launches0;
+  EncodeWs& w = e->ews;
+  if (!e->use_graph || e->prof_on) {                       // eager (per-launch profiling needs real launches)
+    STK_TRY(encoder_features(e, x0_dev, B, s));
+    STK_TRY(run_vq(e, w.q, R, tokens_dev, outs_q_dev ? outs_q_dev : w.outs_q, s));
+    e->last_launches = g_launch_count - launches0;
+  } else {
+    // one CUDA graph per batch size over the workspace's own input / output buffers (the ~250 launches of the 16 dual blocks
+    // dominate a small-batch encode when issued one by one); the caller's buffers are copied in and out around the replay
+    const int64_t nlat = (int64_t)B * e->cfg.in_channels * e->cfg.latent * e->cfg.latent;
+    if (x0_dev != w.x0) STK_CUDA(cudaMemcpyAsync(w.x0, x0_dev, sizeof(float) * nlat, cudaMemcpyDeviceToDevice, s));
+    auto it = e->enc_graphs.find(B);
+    if (it == e->enc_graphs.end()) {
+      cudaStream_t cs;
+      STK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      {
+        const cudaError_t be = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        if (be != cudaSuccess) {
+          cudaStreamDestroy(cs);
+          STK_CUDA(be);
+        }
+      }
+      const int64_t l0 = g_launch_count;
+      int st = encoder_features(e, w.x0, B, cs);
+      if (!st) st = run_vq(e, w.q, R, w.tokens, w.outs_q, cs);
+      cudaGraph_t graph = nullptr;
+      cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+      cudaStreamDestroy(cs);
+      if (st != 0) { if (graph) cudaGraphDestroy(graph); return st; }
+      STK_CUDA(ce);
+      cudaGraphExec_t exec;
+      STK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = e->enc_graphs.emplace(B, std::make_pair(exec, g_launch_count - l0)).first;
+    }
+    STK_CUDA(cudaGraphLaunch(it->second.first, s));
+    e->last_launches = it->second.second;
+    if (tokens_dev != w.tokens) STK_CUDA(cudaMemcpyAsync(tokens_dev, w.tokens, sizeof(int64_t) * R, cudaMemcpyDeviceToDevice, s));
+    if (outs_q_dev && outs_q_dev != w.outs_q)
+      STK_CUDA(cudaMemcpyAsync(outs_q_dev, w.outs_q, sizeof(float) * R * e->cfg.code_dim, cudaMemcpyDeviceToDevice, s));
+  }
+  if (feats_dev) STK_CUDA(cudaMemcpyAsync(feats_dev, w.q, sizeof(float) * R * e->cfg.enc_qdim, cudaMemcpyDeviceToDevice, s));
   return SELFTOK_OK;
 }
 
