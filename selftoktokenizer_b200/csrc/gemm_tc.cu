@@ -268,6 +268,7 @@ struct GemmParams {
   // tap (dy, dx) reads phase (dy & 1, dx & 1) shifted by (dy >> 1, dx >> 1) -- unit-stride boxes again, the zero fill past the last
   // row / column is the one-sided padding.  conv_H / conv_W are the OUTPUT dims.
   int conv_C = 0, conv_H = 0, conv_W = 0, conv_stride = 1;
+  int raster_gm = 4;     // pair-rows per raster group of the SM-pair kernel (pair_coords)
 };
 
 __device__ __forceinline__ void tile_coords(int t, int m_tiles, int n_tiles, int& m_blk, int& n_blk) {
@@ -481,8 +482,9 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t
       ::"r"(local_bar), "r"(rank) : "memory");
 }
 
-__device__ __forceinline__ void pair_coords(int t, int pm_tiles, int n_tiles, int& pm, int& n_blk) {
-  constexpr int GM = 4;                                   // 4 pair-rows = 1024 A rows share each W tile in L2
+__device__ __forceinline__ void pair_coords(int t, int pm_tiles, int n_tiles, int GM, int& pm, int& n_blk) {
+  // GM pair-rows (default 4 = 1024 A rows) share each W tile in L2; SELFTOK_GEMM_GM is a measurement knob (any value is a
+  // bijection of the tile list, results never change)
   const int per_group = GM * n_tiles;
   const int group = t / per_group;
   const int first = group * GM;
@@ -552,8 +554,8 @@ gemm_tc2_kernel(const __grid_constant__ TcMaps maps0, const __grid_constant__ Tc
         const bool second = t >= tiles0;
         const TcMaps& mp = second ? maps1 : maps0;
         int pm, n_blk;
-        if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, pm, n_blk);
-        else pair_coords(t, pm_tiles0, n_tiles0, pm, n_blk);
+        if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, p1.raster_gm, pm, n_blk);
+        else pair_coords(t, pm_tiles0, n_tiles0, p0.raster_gm, pm, n_blk);
         const GemmParams& pp = second ? p1 : p0;
         const int nk = (pp.K + BK - 1) / BK;
         const int m_row = pm * 2 * BM + (int)rank * BM;            // this CTA's 128 A rows
@@ -633,8 +635,8 @@ gemm_tc2_kernel(const __grid_constant__ TcMaps maps0, const __grid_constant__ Tc
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const bool second = t >= tiles0;
       int pm, n_blk;
-      if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, pm, n_blk);
-      else pair_coords(t, pm_tiles0, n_tiles0, pm, n_blk);
+      if (second) pair_coords(t - tiles0, pm_tiles1, n_tiles1, p1.raster_gm, pm, n_blk);
+      else pair_coords(t, pm_tiles0, n_tiles0, p0.raster_gm, pm, n_blk);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int64_t m_base = (int64_t)pm * 2 * BM + (int64_t)rank * BM + quarter * 32;
@@ -677,6 +679,7 @@ EncodeTiledFn g_encode = nullptr;
 constexpr int kMaxDev = 64;
 int g_num_sms_dev[kMaxDev];
 bool g_attr_dev[kMaxDev];
+int g_raster_gm = 4;      // SELFTOK_GEMM_GM (measurement knob)
 int g_gemm_ctas = 2;      // 2: cta_group::2 pair kernel (default); 1: single-CTA kernel (SELFTOK_GEMM_CTAS=1)
 
 int make_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows, int K, int box_rows, int fp16) {
@@ -750,6 +753,8 @@ int gemm_tc_init() {
     STK_CHECK(fn && qres == cudaDriverEntryPointSuccess, -5, "cuTensorMapEncodeTiled not available from the driver");
     const char* v = getenv("SELFTOK_GEMM_CTAS");
     if (v) g_gemm_ctas = atoi(v) == 1 ? 1 : 2;
+    const char* gm = getenv("SELFTOK_GEMM_GM");
+    if (gm && atoi(gm) >= 1 && atoi(gm) <= 1024) g_raster_gm = atoi(gm);
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
   STK_CUDA(cudaDeviceGetAttribute(&g_num_sms_dev[dev], cudaDevAttrMultiProcessorCount, dev));
@@ -830,6 +835,7 @@ int launch_gemm_tc_grouped(const TcProblem* probs, int n, int nsplit, cudaStream
   auto mk_params = [&](const TcProblem& q) {
     GemmParams g{q.M, q.N, q.K, fp16, q.ep};
     g.conv_C = q.conv_C; g.conv_H = q.conv_H; g.conv_W = q.conv_W; g.conv_stride = q.conv_stride;
+    g.raster_gm = g_raster_gm;
     return g;
   };
   GemmParams p0 = mk_params(probs[0]);

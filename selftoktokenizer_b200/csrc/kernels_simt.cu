@@ -775,29 +775,61 @@ __global__ void __launch_bounds__(256) vq_kernel(const float* __restrict__ z, in
     const int buf = ch & 1;
     if (ch + 1 < nch) { issue(ch + 1, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncthreads();
+    // scores of this thread's 4 rows x 8 codes as packed pairs (acc[i][2 j2], acc[i][2 j2 + 1]) on FFMA2 (fma.rn.f32x2: two
+    // independent round-to-nearest FMAs per issue slot, the same d order -> bit-identical to the scalar fmaf chain): the scalar
+    // version was issue-bound (ncu: issue 73 %, FMA pipe 51 %), the packed one leaves the slots to the LDS.128 and the argmax
+    unsigned long long acc2[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
+#pragma unroll
+    for (int d = 0; d < VQ_DIM; ++d) {
+      const ulonglong2 c0 = *reinterpret_cast<const ulonglong2*>(&cs[buf][d][tx * 4]);
+      const ulonglong2 c1 = *reinterpret_cast<const ulonglong2*>(&cs[buf][d][64 + tx * 4]);
+      const unsigned long long cv2[4] = {c0.x, c0.y, c1.x, c1.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        unsigned long long xd;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(xd) : "f"(xr[i][d]));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(xd), "l"(cv2[j]));
+      }
+    }
     float acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-#pragma unroll
-    for (int d = 0; d < VQ_DIM; ++d) {
-      float4 c0 = *reinterpret_cast<const float4*>(&cs[buf][d][tx * 4]);
-      float4 c1 = *reinterpret_cast<const float4*>(&cs[buf][d][64 + tx * 4]);
-      float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i][d], cv[j], acc[i][j]);
-    }
+      for (int j = 0; j < 4; ++j) {
+        acc[i][2 * j] = __uint_as_float((uint32_t)acc2[i][j]);
+        acc[i][2 * j + 1] = __uint_as_float((uint32_t)(acc2[i][j] >> 32));
+      }
     const int base = ch * VQ_CH;
+    if (base + VQ_CH <= n_codes) {
+      // whole chunk valid: one max tree per row; the (rare: ~ln(#chunks) times per row) improvement then looks up the FIRST code
+      // that attains it -- j ascending is code ascending, so this is the same winner as a strict-> scan in code order
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int code = base + (j / 4) * 64 + tx * 4 + (j % 4);
-      if (code < n_codes) {
+      for (int i = 0; i < 4; ++i) {
+        const float m = fmaxf(fmaxf(fmaxf(acc[i][0], acc[i][1]), fmaxf(acc[i][2], acc[i][3])),
+                              fmaxf(fmaxf(acc[i][4], acc[i][5]), fmaxf(acc[i][6], acc[i][7])));
+        if (m > best[i]) {
+          best[i] = m;
+          int jj = 7;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (acc[i][j] > best[i]) { best[i] = acc[i][j]; besti[i] = code; }   // strict >: first maximum wins
+          for (int j = 6; j >= 0; --j)
+            if (acc[i][j] == m) jj = j;
+          besti[i] = base + (jj / 4) * 64 + tx * 4 + (jj % 4);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int code = base + (j / 4) * 64 + tx * 4 + (j % 4);
+        if (code < n_codes) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (acc[i][j] > best[i]) { best[i] = acc[i][j]; besti[i] = code; }   // strict >: first maximum wins
+        }
       }
     }
     __syncthreads();
