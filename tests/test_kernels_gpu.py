@@ -20,7 +20,8 @@ def _rand(shape, seed, dev, scale=1.0):
 
 
 @pytest.mark.parametrize("M,N,K,act", [(300, 192, 64, 0), (1000, 1536, 512, 1), (64, 64, 256, 2), (4096, 64, 1536, 0),
-                                        (37, 3072, 512, 0), (512, 16, 512, 0), (130, 130, 16, 0)])
+                                        (37, 3072, 512, 0), (512, 16, 512, 0), (130, 130, 16, 0),
+                                        (300, 520, 132, 0), (129, 260, 1024, 1)])    # ragged M / N / K on the 128 x 256 tile
 def test_linear_f32(dev, M, N, K, act):
     from selftoktokenizer_b200 import capi
     A, W, b = _rand((M, K), 1, dev), _rand((N, K), 2, dev, 1 / math.sqrt(K)), _rand((N,), 3, dev)
