@@ -6,11 +6,12 @@ Same constructor signature, attributes and method contracts as the reference cla
     decoding(idx numpy [B,K] int64, device)                 -> images [B,3,H,W] in [0,1], self.dtype (:227-294)
     decoding_with_renderer(idx, device)                     -> same, one renderer pass               (:296-322)
 
-Everything between the VAE calls runs in the CUDA library behind include/selftok_b200.h; the host keeps what the
-reference keeps on the host: YAML/config, checkpoint loading, the SD3 VAE (diffusers; outside the measured path,
-SURVEY 8f), the CPU-generator noise draw (:262-264) and numpy<->tensor conversion.  The latent-boundary methods
-`encode_latents` / `decode_latents` / `render_latents` are the same calls without the VAE and are what the parity
-tests and bench.py measure.
+Everything between the pixel tensors runs in the CUDA library behind include/selftok_b200.h -- the encoder / VQ / sampler /
+renderer engine and, through `DeviceVAE`, both halves of the SD3 VAE (diffusers' AutoencoderKL is only the
+source of the VAE weights and the fallback for image sides other than 128 / 256 / 512).  The host keeps what the reference
+keeps on the host: YAML/config, checkpoint loading, the CPU-generator noise draw (:262-264) and numpy<->tensor conversion.
+The latent-boundary methods `encode_latents` / `decode_latents` / `render_latents` are the same calls without the VAE and are
+what the headline of bench.py measures (its `extra.pixel_e2e` record goes through `encoding` / `decoding`).
 
 Reference quirks consciously NOT reproduced (documented in DESIGN.md): cfg is not mutated; the sampler does not
 re-run encoder+VQ on the noise every step (rectified_flow.py:212-215, dead for the output); quantizer.steps/count
