@@ -130,7 +130,7 @@ def test_pipeline_api_latent_boundary(tiny_sd, gold):
 # A second reduced geometry with deliberately ragged sizes (K = 40 tokens, 6x6 = 36 image tokens, S = 41..76, rows not multiples of
 # any tile): no reference fixture, so the checker is the (pinned) oracle run on the CPU in the same test.
 RAGGED = dataclasses.replace(C.TINY, K=40, k_per_stage=(14, 10, 8, 5, 3), latent=12, enc_pos_max=24, dit_pos_max=10, enc_depth=1,
-                             dit_depth=2, codebook_size=2048)
+                             dit_depth=2, codebook_size=2040)      # 15 full 128-code chunks + a 120-code tail: both argmax paths of vq_kernel
 
 
 @pytest.mark.parametrize("precision", ["bf16x3", "fp16"])
